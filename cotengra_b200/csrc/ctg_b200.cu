@@ -1,0 +1,619 @@
+// ctg_b200.cu -- C-ABI implementation (include/ctg_b200.h): kernel dispatch, the
+// per-slice node loop and the slice loop, all on the device stream.
+//
+// Reference path replaced:
+//   Contractor.__call__ node loop ........ cotengra/contract.py:791-832
+//   ContractionTree.contract slice loop .. cotengra/core.py:4015-4030
+//   slice_key / slice_arrays ............. cotengra/core.py:3775-3819
+//   gather_slices (sum and stack) ........ cotengra/core.py:3825-3882
+//   contract_mpi round robin ............. cotengra/core.py:4070
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <atomic>
+#include <type_traits>
+#include <string>
+#include <vector>
+
+#include "../../include/ctg_b200.h"
+#include "gett_desc.h"
+#include "gett_kernels.cuh"
+#include "probe.cuh"
+
+using namespace ctgb;
+
+namespace {
+
+thread_local std::string g_err;
+std::atomic<int64_t> g_launches{0};
+
+int fail(int code, const std::string& msg) {
+  g_err = msg;
+  return code;
+}
+#define CUDA_TRY(expr)                                                                       \
+  do {                                                                                       \
+    cudaError_t _e = (expr);                                                                 \
+    if (_e != cudaSuccess)                                                                   \
+      return fail(CTGB_E_CUDA, std::string(#expr) + ": " + cudaGetErrorString(_e));          \
+  } while (0)
+
+struct DevInfo {
+  bool ok = false;
+  int sms = 0, major = 0, minor = 0;
+  size_t smem_optin = 0;
+};
+DevInfo& devinfo() {
+  static thread_local DevInfo d;
+  static thread_local int cached_dev = -1;
+  int dev = -1;
+  if (cudaGetDevice(&dev) != cudaSuccess) {
+    d.ok = false;
+    return d;
+  }
+  if (dev != cached_dev) {
+    cudaDeviceProp p;
+    if (cudaGetDeviceProperties(&p, dev) == cudaSuccess) {
+      d.ok = true;
+      d.sms = p.multiProcessorCount;
+      d.major = p.major;
+      d.minor = p.minor;
+      d.smem_optin = p.sharedMemPerBlockOptin;
+      cached_dev = dev;
+    } else {
+      d.ok = false;
+    }
+  }
+  return d;
+}
+
+size_t elem_size(int dtype) {
+  switch (dtype) {
+    case CTGB_F32: return 4;
+    case CTGB_F64: return 8;
+    case CTGB_C64: return 8;
+    case CTGB_C128: return 16;
+  }
+  return 0;
+}
+
+// ---------------------------------------------------------------- dispatch
+template <typename T, class P>
+int launch_gett_policy(const int64_t* h, const int64_t* d, const void* A, const void* B, void* C, cudaStream_t st) {
+  DevInfo& di = devinfo();
+  if (!di.ok) return fail(CTGB_E_CUDA, "no CUDA device");
+  constexpr size_t smem = GettSmem<P>::template bytes<T>();
+  if (smem > di.smem_optin) return fail(CTGB_E_CUDA, "kernel variant needs more shared memory than the device offers");
+  static thread_local int attr_dev = -1;
+  int dev;
+  cudaGetDevice(&dev);
+  if (attr_dev != dev) {
+    CUDA_TRY(cudaFuncSetAttribute(gett_kernel<T, P>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr_dev = dev;
+  }
+  static thread_local int occ = 0;
+  if (occ == 0) {
+    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, gett_kernel<T, P>, P::THREADS, smem));
+    if (occ < 1) occ = 1;
+  }
+  const uint64_t work = (uint64_t)h[W_TILES_M] * (uint64_t)h[W_TILES_N] * (uint64_t)h[W_TILES_B] * (uint64_t)h[W_SPLITK];
+  if (work == 0) return CTGB_OK;
+  if (work >= (1ull << 31)) return fail(CTGB_E_VALUE, "too many tiles for one launch");
+  uint64_t grid = (uint64_t)di.sms * occ;
+  if (grid > work) grid = work;
+  if (h[W_SPLITK] > 1 && !(h[W_FLAGS] & 1)) {
+    if (h[W_CELEMS] <= 0) return fail(CTGB_E_VALUE, "split-K into a strided C needs accumulate");
+    CUDA_TRY(cudaMemsetAsync(C, 0, (size_t)h[W_CELEMS] * sizeof(T), st));
+  }
+  gett_kernel<T, P><<<(unsigned)grid, P::THREADS, smem, st>>>(d, (const T*)A, (const T*)B, (T*)C);
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  CUDA_TRY(cudaGetLastError());
+  return CTGB_OK;
+}
+
+template <typename T>
+int launch_gett_typed(const int64_t* h, const int64_t* d, const void* A, const void* B, void* C, cudaStream_t st) {
+  const int variant = (int)h[W_VARIANT];
+  switch (variant) {
+    case VAR_SIMT_64x64: return launch_gett_policy<T, SimtPolicy<T, 64, 64, 8, 3>>(h, d, A, B, C, st);
+    case VAR_KRED: return launch_gett_policy<T, KredPolicy<T, 1, 1, 1024, 3>>(h, d, A, B, C, st);
+    default: break;
+  }
+  if constexpr (sizeof(T) == 16 || (sizeof(T) == 8 && std::is_same<T, double>::value)) {
+    switch (variant) {
+      case VAR_DMMA_128x64: return launch_gett_policy<T, DmmaPolicy<T, 4, 2, 4, 4, 16, 3>>(h, d, A, B, C, st);
+      case VAR_DMMA_64x128: return launch_gett_policy<T, DmmaPolicy<T, 2, 4, 4, 4, 16, 3>>(h, d, A, B, C, st);
+      case VAR_DMMA_256x32: return launch_gett_policy<T, DmmaPolicy<T, 8, 1, 4, 4, 8, 3>>(h, d, A, B, C, st);
+      default: break;
+    }
+  }
+  return fail(CTGB_E_VALUE, "unknown kernel variant for this dtype");
+}
+
+int launch_gett(const int64_t* h, const int64_t* d, const void* A, const void* B, void* C, cudaStream_t st) {
+  if (h[W_MAGIC] != DESC_MAGIC) return fail(CTGB_E_VALUE, "bad pair descriptor magic");
+  switch ((int)h[W_DTYPE]) {
+    case CTGB_F32: return launch_gett_typed<float>(h, d, A, B, C, st);
+    case CTGB_F64: return launch_gett_typed<double>(h, d, A, B, C, st);
+    case CTGB_C64: return launch_gett_typed<float2>(h, d, A, B, C, st);
+    case CTGB_C128: return launch_gett_typed<double2>(h, d, A, B, C, st);
+  }
+  return fail(CTGB_E_VALUE, "bad dtype");
+}
+
+template <typename T>
+int launch_single_typed(const int64_t* h, const int64_t* d, const void* X, void* out, cudaStream_t st) {
+  long long n = h[S_OUT_ELEMS];
+  if (n <= 0) return CTGB_OK;
+  long long blocks = (n + 255) / 256;
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  single_kernel<T><<<(unsigned)blocks, 256, 0, st>>>(d, (const T*)X, (T*)out);
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  CUDA_TRY(cudaGetLastError());
+  return CTGB_OK;
+}
+int launch_single(const int64_t* h, const int64_t* d, const void* X, void* out, cudaStream_t st) {
+  if (h[S_MAGIC] != SDESC_MAGIC) return fail(CTGB_E_VALUE, "bad single descriptor magic");
+  switch ((int)h[S_DTYPE]) {
+    case CTGB_F32: return launch_single_typed<float>(h, d, X, out, st);
+    case CTGB_F64: return launch_single_typed<double>(h, d, X, out, st);
+    case CTGB_C64: return launch_single_typed<float2>(h, d, X, out, st);
+    case CTGB_C128: return launch_single_typed<double2>(h, d, X, out, st);
+  }
+  return fail(CTGB_E_VALUE, "bad dtype");
+}
+
+unsigned flat_grid(long long n) {
+  long long b = (n + 255) / 256;
+  if (b > 148 * 8) b = 148 * 8;
+  if (b < 1) b = 1;
+  return (unsigned)b;
+}
+
+template <typename T>
+int strip_typed(void* p, long long n, unsigned long long* slot, double* exponent, cudaStream_t st) {
+  zero_slot_kernel<<<1, 1, 0, st>>>(slot);
+  absmax_kernel<T><<<flat_grid(n), 256, 0, st>>>((const T*)p, n, slot);
+  strip_kernel<T><<<flat_grid(n), 256, 0, st>>>((T*)p, n, slot, exponent);
+  g_launches.fetch_add(3, std::memory_order_relaxed);
+  CUDA_TRY(cudaGetLastError());
+  return CTGB_OK;
+}
+int strip(int dtype, void* p, long long n, unsigned long long* slot, double* exponent, cudaStream_t st) {
+  switch (dtype) {
+    case CTGB_F32: return strip_typed<float>(p, n, slot, exponent, st);
+    case CTGB_F64: return strip_typed<double>(p, n, slot, exponent, st);
+    case CTGB_C64: return strip_typed<float2>(p, n, slot, exponent, st);
+    case CTGB_C128: return strip_typed<double2>(p, n, slot, exponent, st);
+  }
+  return fail(CTGB_E_VALUE, "bad dtype");
+}
+
+template <typename T>
+int accum_stripped_typed(const int64_t* dchunk, const int64_t* hchunk, void* out, void* chunk, long long out_elems,
+                         const void* m, double* E, const double* es, cudaStream_t st) {
+  rescale_out_kernel<T><<<flat_grid(out_elems), 256, 0, st>>>((T*)out, out_elems, E, es);
+  add_chunk_kernel<T><<<flat_grid(hchunk[S_OUT_ELEMS]), 256, 0, st>>>(dchunk, (T*)chunk, (const T*)m, E, es);
+  commit_exponent_kernel<<<1, 1, 0, st>>>(E, es);
+  g_launches.fetch_add(3, std::memory_order_relaxed);
+  CUDA_TRY(cudaGetLastError());
+  return CTGB_OK;
+}
+int accum_stripped(int dtype, const int64_t* dchunk, const int64_t* hchunk, void* out, void* chunk,
+                   long long out_elems, const void* m, double* E, const double* es, cudaStream_t st) {
+  switch (dtype) {
+    case CTGB_F32: return accum_stripped_typed<float>(dchunk, hchunk, out, chunk, out_elems, m, E, es, st);
+    case CTGB_F64: return accum_stripped_typed<double>(dchunk, hchunk, out, chunk, out_elems, m, E, es, st);
+    case CTGB_C64: return accum_stripped_typed<float2>(dchunk, hchunk, out, chunk, out_elems, m, E, es, st);
+    case CTGB_C128: return accum_stripped_typed<double2>(dchunk, hchunk, out, chunk, out_elems, m, E, es, st);
+  }
+  return fail(CTGB_E_VALUE, "bad dtype");
+}
+
+}  // namespace
+
+// ================================================================== plans
+struct ctgb_plan {
+  int dtype = 0;
+  int n_inputs = 0;
+  struct Tensor {
+    int kind, input_index;
+    int64_t offset, nbytes;
+    std::vector<int32_t> slice_pos;
+    std::vector<int64_t> slice_stride;
+  };
+  struct Node {
+    int kind, a, b, c, invariant, is_root;
+    size_t desc_off;  // word offset into descs
+    int64_t c_elems;  // dense elements of the result (strip_exponent)
+  };
+  std::vector<Tensor> tensors;
+  std::vector<Node> nodes;
+  std::vector<int64_t> descs;  // host copy of every descriptor, concatenated
+  int64_t* d_descs = nullptr;
+  std::vector<int64_t> radix, project, out_stride;
+  int64_t out_elements = 0, workspace_bytes = 0, persistent_bytes = 0;
+  int strip_exponent = 0;
+  int64_t launches_per_slice = 0;
+  // strip_exponent scratch (device): [0] factor slot, [1] slice exponent, [2] invariant exponent
+  double* d_scalars = nullptr;
+  // chunk descriptor for stripped accumulation (host + device), built at create
+  std::vector<int64_t> chunk_desc;
+  int64_t* d_chunk_desc = nullptr;
+  int device = -1;
+  // optional per-node timing (bench.py roofline): events around every node launch
+  bool profile = false;
+  std::vector<cudaEvent_t> ev0, ev1;
+};
+
+extern "C" {
+
+int ctgb_abi_version(void) { return CTGB_ABI_VERSION; }
+int ctgb_desc_words(void) { return DESC_WORDS; }
+int ctgb_single_desc_words(void) { return SDESC_WORDS; }
+const char* ctgb_last_error(void) { return g_err.c_str(); }
+int64_t ctgb_launch_count(void) { return g_launches.load(); }
+
+int ctgb_device_info(int* sm_count, int* cc_major, int* cc_minor, size_t* smem_optin_bytes) {
+  DevInfo& d = devinfo();
+  if (!d.ok) return fail(CTGB_E_CUDA, "no CUDA device");
+  if (sm_count) *sm_count = d.sms;
+  if (cc_major) *cc_major = d.major;
+  if (cc_minor) *cc_minor = d.minor;
+  if (smem_optin_bytes) *smem_optin_bytes = d.smem_optin;
+  return CTGB_OK;
+}
+
+int ctgb_probe_fp64_peaks(double* dmma_tflops, double* dfma_tflops, void* stream) {
+  DevInfo& di = devinfo();
+  if (!di.ok) return fail(CTGB_E_CUDA, "no CUDA device");
+  cudaStream_t st = (cudaStream_t)stream;
+  double* sink = nullptr;
+  CUDA_TRY(cudaMalloc((void**)&sink, 64));
+  cudaEvent_t e0, e1;
+  CUDA_TRY(cudaEventCreate(&e0));
+  CUDA_TRY(cudaEventCreate(&e1));
+  const int blocks = di.sms * 8, iters = 4096;
+  auto timed = [&](int which, double flop_per_thread_iter, double* out) -> int {
+    float best = 1e30f;
+    for (int rep = 0; rep < 4; ++rep) {
+      CUDA_TRY(cudaEventRecord(e0, st));
+      if (which == 0) probe_dmma_kernel<<<blocks, 256, 0, st>>>(sink, iters);
+      else probe_dfma_kernel<<<blocks, 256, 0, st>>>(sink, iters);
+      CUDA_TRY(cudaEventRecord(e1, st));
+      CUDA_TRY(cudaEventSynchronize(e1));
+      float ms = 0.f;
+      CUDA_TRY(cudaEventElapsedTime(&ms, e0, e1));
+      if (rep > 0 && ms < best) best = ms;
+    }
+    g_launches.fetch_add(4, std::memory_order_relaxed);
+    *out = flop_per_thread_iter * iters * 256.0 * blocks / (best * 1e-3) / 1e12;
+    return CTGB_OK;
+  };
+  int rc = CTGB_OK;
+  // one DMMA = 8*8*4 MACs per warp = 512 flop / 32 lanes; 8 per iteration
+  if (dmma_tflops) rc = timed(0, 8 * 512.0 / 32.0, dmma_tflops);
+  if (!rc && dfma_tflops) rc = timed(1, 8 * 2.0, dfma_tflops);
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  cudaFree(sink);
+  return rc;
+}
+
+int ctgb_contract_pair(const int64_t* desc, const void* A, const void* B, void* C, void* stream) {
+  if (!desc) return fail(CTGB_E_VALUE, "null descriptor");
+  cudaStream_t st = (cudaStream_t)stream;
+  int64_t* d = nullptr;
+  CUDA_TRY(cudaMallocAsync((void**)&d, DESC_WORDS * sizeof(int64_t), st));
+  CUDA_TRY(cudaMemcpyAsync(d, desc, DESC_WORDS * sizeof(int64_t), cudaMemcpyHostToDevice, st));
+  int rc = launch_gett(desc, d, A, B, C, st);
+  cudaFreeAsync(d, st);
+  return rc;
+}
+
+int ctgb_reduce_single(const int64_t* desc, const void* X, void* out, void* stream) {
+  if (!desc) return fail(CTGB_E_VALUE, "null descriptor");
+  cudaStream_t st = (cudaStream_t)stream;
+  int64_t* d = nullptr;
+  CUDA_TRY(cudaMallocAsync((void**)&d, SDESC_WORDS * sizeof(int64_t), st));
+  CUDA_TRY(cudaMemcpyAsync(d, desc, SDESC_WORDS * sizeof(int64_t), cudaMemcpyHostToDevice, st));
+  int rc = launch_single(desc, d, X, out, st);
+  cudaFreeAsync(d, st);
+  return rc;
+}
+
+int ctgb_plan_create(const ctgb_plan_desc* pd, ctgb_plan** out) {
+  if (!pd || !out) return fail(CTGB_E_VALUE, "null argument");
+  if (elem_size(pd->dtype) == 0) return fail(CTGB_E_VALUE, "bad dtype");
+  ctgb_plan* p = new ctgb_plan();
+  p->dtype = pd->dtype;
+  p->n_inputs = pd->n_inputs;
+  p->tensors.resize(pd->n_tensors);
+  for (int i = 0; i < pd->n_tensors; ++i) {
+    const ctgb_tensor& t = pd->tensors[i];
+    auto& q = p->tensors[i];
+    q.kind = t.kind;
+    q.input_index = t.input_index;
+    q.offset = t.offset;
+    q.nbytes = t.nbytes;
+    if (t.kind == 0 && (t.input_index < 0 || t.input_index >= pd->n_inputs)) {
+      delete p;
+      return fail(CTGB_E_VALUE, "tensor refers to a missing input");
+    }
+    for (int j = 0; j < t.n_sliced; ++j) {
+      if (t.slice_pos[j] < 0 || t.slice_pos[j] >= pd->n_sliced) {
+        delete p;
+        return fail(CTGB_E_VALUE, "slice position out of range");
+      }
+      q.slice_pos.push_back(t.slice_pos[j]);
+      q.slice_stride.push_back(t.slice_stride[j]);
+    }
+  }
+  p->nodes.resize(pd->n_nodes);
+  int64_t per_slice = 0;
+  for (int i = 0; i < pd->n_nodes; ++i) {
+    const ctgb_node& n = pd->nodes[i];
+    auto& q = p->nodes[i];
+    q.kind = n.kind;
+    q.a = n.a;
+    q.b = n.b;
+    q.c = n.c;
+    q.invariant = n.invariant;
+    q.is_root = n.is_root;
+    const int words = n.kind == 0 ? DESC_WORDS : SDESC_WORDS;
+    const int64_t magic = n.kind == 0 ? DESC_MAGIC : SDESC_MAGIC;
+    if (!n.desc || n.desc[0] != magic) {
+      delete p;
+      return fail(CTGB_E_VALUE, "bad node descriptor");
+    }
+    auto bad = [&](int t) { return t < 0 || t >= pd->n_tensors; };
+    if (bad(n.a) || bad(n.c) || (n.kind == 0 && bad(n.b))) {
+      delete p;
+      return fail(CTGB_E_VALUE, "node refers to a missing tensor");
+    }
+    q.desc_off = p->descs.size();
+    p->descs.insert(p->descs.end(), n.desc, n.desc + words);
+    q.c_elems = p->tensors[n.c].nbytes / (int64_t)elem_size(pd->dtype);
+    if (!n.invariant) per_slice += 1 + (pd->strip_exponent ? 3 : 0);
+  }
+  p->launches_per_slice = per_slice;
+  p->radix.assign(pd->slice_radix, pd->slice_radix + pd->n_sliced);
+  p->project.assign(pd->slice_project, pd->slice_project + pd->n_sliced);
+  p->out_stride.assign(pd->slice_out_stride, pd->slice_out_stride + pd->n_sliced);
+  p->out_elements = pd->out_elements;
+  p->workspace_bytes = pd->workspace_bytes;
+  p->persistent_bytes = pd->persistent_bytes;
+  p->strip_exponent = pd->strip_exponent;
+
+  if (cudaGetDevice(&p->device) != cudaSuccess) {
+    delete p;
+    return fail(CTGB_E_CUDA, "no CUDA device");
+  }
+  cudaError_t e = cudaMalloc((void**)&p->d_descs, p->descs.size() * sizeof(int64_t) + 8);
+  if (e == cudaSuccess)
+    e = cudaMemcpy(p->d_descs, p->descs.data(), p->descs.size() * sizeof(int64_t), cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) e = cudaMalloc((void**)&p->d_scalars, 8 * sizeof(double));
+  if (e == cudaSuccess) e = cudaMemset(p->d_scalars, 0, 8 * sizeof(double));
+  if (e != cudaSuccess) {
+    std::string msg = cudaGetErrorString(e);
+    ctgb_plan_destroy(p);
+    return fail(CTGB_E_CUDA, "plan upload: " + msg);
+  }
+  *out = p;
+  return CTGB_OK;
+}
+
+int ctgb_plan_profile(ctgb_plan* p, int enable) {
+  if (!p) return fail(CTGB_E_VALUE, "null plan");
+  if (enable && p->ev0.empty()) {
+    p->ev0.resize(p->nodes.size());
+    p->ev1.resize(p->nodes.size());
+    for (size_t i = 0; i < p->nodes.size(); ++i) {
+      CUDA_TRY(cudaEventCreate(&p->ev0[i]));
+      CUDA_TRY(cudaEventCreate(&p->ev1[i]));
+    }
+  }
+  p->profile = enable != 0;
+  return CTGB_OK;
+}
+
+int ctgb_plan_profile_read(ctgb_plan* p, float* ms, int n_nodes) {
+  if (!p || !ms) return fail(CTGB_E_VALUE, "null argument");
+  if (p->ev0.empty()) return fail(CTGB_E_VALUE, "profiling was never enabled");
+  if (n_nodes != (int)p->nodes.size()) return fail(CTGB_E_VALUE, "node count mismatch");
+  for (int i = 0; i < n_nodes; ++i) {
+    ms[i] = -1.f;
+    if (cudaEventQuery(p->ev1[i]) == cudaErrorInvalidResourceHandle) continue;
+    cudaError_t e = cudaEventSynchronize(p->ev1[i]);
+    if (e != cudaSuccess) { cudaGetLastError(); continue; }
+    float t = 0.f;
+    if (cudaEventElapsedTime(&t, p->ev0[i], p->ev1[i]) == cudaSuccess) ms[i] = t; else cudaGetLastError();
+  }
+  return CTGB_OK;
+}
+
+void ctgb_plan_destroy(ctgb_plan* p) {
+  if (!p) return;
+  for (auto e : p->ev0) cudaEventDestroy(e);
+  for (auto e : p->ev1) cudaEventDestroy(e);
+  if (p->d_descs) cudaFree(p->d_descs);
+  if (p->d_scalars) cudaFree(p->d_scalars);
+  if (p->d_chunk_desc) cudaFree(p->d_chunk_desc);
+  delete p;
+}
+
+size_t ctgb_plan_workspace_bytes(const ctgb_plan* p) {
+  return p ? (size_t)(p->workspace_bytes + p->persistent_bytes) : 0;
+}
+int64_t ctgb_plan_launches_per_slice(const ctgb_plan* p) { return p ? p->launches_per_slice : 0; }
+
+// Install the (single-operand style) descriptor that maps the dense root result
+// of one slice onto its chunk of the full output; only used with strip_exponent.
+int ctgb_plan_set_chunk_desc(ctgb_plan* p, const int64_t* desc) {
+  if (!p || !desc || desc[0] != SDESC_MAGIC) return fail(CTGB_E_VALUE, "bad chunk descriptor");
+  p->chunk_desc.assign(desc, desc + SDESC_WORDS);
+  if (!p->d_chunk_desc) CUDA_TRY(cudaMalloc((void**)&p->d_chunk_desc, SDESC_WORDS * sizeof(int64_t)));
+  CUDA_TRY(cudaMemcpy(p->d_chunk_desc, desc, SDESC_WORDS * sizeof(int64_t), cudaMemcpyHostToDevice));
+  return CTGB_OK;
+}
+
+int ctgb_plan_execute(ctgb_plan* p, const void* const* inputs, void* out, double* exponent_dev, void* workspace,
+                      size_t workspace_bytes, int64_t slice_begin, int64_t slice_step, int64_t slice_count,
+                      void* stream) {
+  if (!p) return fail(CTGB_E_VALUE, "null plan");
+  if (workspace_bytes < (size_t)(p->workspace_bytes + p->persistent_bytes))
+    return fail(CTGB_E_MEMORY, "workspace too small");
+  if (p->strip_exponent && (!exponent_dev || p->chunk_desc.empty()))
+    return fail(CTGB_E_VALUE, "strip_exponent needs an exponent buffer and a chunk descriptor");
+  cudaStream_t st = (cudaStream_t)stream;
+  const size_t es = elem_size(p->dtype);
+  char* persistent = (char*)workspace;
+  char* scratch = persistent + p->persistent_bytes;
+  const int ns = (int)p->radix.size();
+  std::vector<int64_t> digits(ns, 0);
+
+  unsigned long long* d_slot = (unsigned long long*)(p->d_scalars + 0);
+  double* d_slice_exp = p->d_scalars + 1;
+  double* d_inv_exp = p->d_scalars + 2;
+
+  auto resolve = [&](int t, int64_t out_off) -> char* {
+    const ctgb_plan::Tensor& q = p->tensors[t];
+    switch (q.kind) {
+      case 0: {
+        int64_t off = 0;
+        for (size_t j = 0; j < q.slice_pos.size(); ++j) off += digits[q.slice_pos[j]] * q.slice_stride[j];
+        return (char*)inputs[q.input_index] + off * (int64_t)es;
+      }
+      case 1: return scratch + q.offset;
+      case 2: return persistent + q.offset;
+      default: return (char*)out + out_off * (int64_t)es;
+    }
+  };
+
+  auto run_nodes = [&](bool invariant_pass, int64_t out_off, double* exp_acc) -> int {
+    for (size_t ni = 0; ni < p->nodes.size(); ++ni) {
+      const auto& n = p->nodes[ni];
+      if ((n.invariant != 0) != invariant_pass) continue;
+      if (p->profile) cudaEventRecord(p->ev0[ni], st);
+      const int64_t* h = p->descs.data() + n.desc_off;
+      const int64_t* d = p->d_descs + n.desc_off;
+      char* A = resolve(n.a, out_off);
+      char* C = resolve(n.c, out_off);
+      int rc;
+      if (n.kind == 0) {
+        char* B = resolve(n.b, out_off);
+        rc = launch_gett(h, d, A, B, C, st);
+      } else {
+        rc = launch_single(h, d, A, C, st);
+      }
+      if (rc) return rc;
+      // contract.py:816-829 strips after every *pairwise* node (single-operand
+      // preprocessing steps `continue` before reaching it, :792-796)
+      if (p->strip_exponent && n.kind == 0) {
+        rc = strip(p->dtype, C, n.c_elems, d_slot, exp_acc, st);
+        if (rc) return rc;
+      }
+      if (p->profile) cudaEventRecord(p->ev1[ni], st);
+    }
+    return CTGB_OK;
+  };
+
+  // slice-invariant subtrees: once per execute call, kept in the persistent arena
+  bool any_inv = false;
+  for (const auto& n : p->nodes) any_inv |= n.invariant != 0;
+  if (p->strip_exponent) {
+    set_double_kernel<<<1, 1, 0, st>>>(d_inv_exp, 0.0);
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+  }
+  if (any_inv) {
+    int rc = run_nodes(true, 0, d_inv_exp);
+    if (rc) return rc;
+  }
+
+  for (int64_t k = 0; k < slice_count; ++k) {
+    // slice id -> digits, most significant first (core.py:3775-3800)
+    int64_t i = slice_begin + k * slice_step;
+    {
+      int64_t rem = i;
+      std::vector<int64_t> strides(ns, 1);
+      for (int j = ns - 2; j >= 0; --j) strides[j] = strides[j + 1] * p->radix[j + 1];
+      for (int j = 0; j < ns; ++j) {
+        if (p->project[j] >= 0) {
+          digits[j] = p->project[j];
+        } else {
+          digits[j] = rem / strides[j];
+          rem %= strides[j];
+        }
+      }
+    }
+    int64_t out_off = 0;
+    for (int j = 0; j < ns; ++j) out_off += digits[j] * p->out_stride[j];
+    if (p->strip_exponent) {
+      copy_double_kernel<<<1, 1, 0, st>>>(d_slice_exp, d_inv_exp);
+      g_launches.fetch_add(1, std::memory_order_relaxed);
+    }
+    int rc = run_nodes(false, out_off, d_slice_exp);
+    if (rc) return rc;
+    if (p->strip_exponent) {
+      // the root wrote a dense mantissa into its workspace slot; fold it into the
+      // output against the running exponent (core.py:163-170, 3856-3861)
+      const ctgb_plan::Node* root = nullptr;
+      for (const auto& n : p->nodes)
+        if (n.is_root) root = &n;
+      if (!root) return fail(CTGB_E_VALUE, "plan has no root node");
+      char* m = resolve(root->c, 0);
+      rc = accum_stripped(p->dtype, p->d_chunk_desc, p->chunk_desc.data(), out, (char*)out + out_off * (int64_t)es,
+                          p->out_elements, m, exponent_dev, d_slice_exp, st);
+      if (rc) return rc;
+    }
+  }
+  return CTGB_OK;
+}
+
+int ctgb_plan_execute_host(ctgb_plan* p, const void* const* host_inputs, const int64_t* input_nbytes, void* host_out,
+                           double* host_exponent, void* workspace, size_t workspace_bytes, int64_t slice_begin,
+                           int64_t slice_step, int64_t slice_count, void* stream) {
+  if (!p) return fail(CTGB_E_VALUE, "null plan");
+  cudaStream_t st = (cudaStream_t)stream;
+  const size_t es = elem_size(p->dtype);
+  const size_t core = (size_t)(p->workspace_bytes + p->persistent_bytes);
+  // staging area at the tail of the workspace: inputs, output, exponent
+  size_t need = core;
+  auto align = [](size_t x) { return (x + 255) & ~(size_t)255; };
+  need = align(need);
+  std::vector<size_t> in_off(p->n_inputs);
+  for (int i = 0; i < p->n_inputs; ++i) {
+    in_off[i] = need;
+    need = align(need + (size_t)input_nbytes[i]);
+  }
+  const size_t out_off = need;
+  need = align(need + (size_t)p->out_elements * es);
+  const size_t exp_off = need;
+  need += 256;
+  if (workspace_bytes < need) return fail(CTGB_E_MEMORY, "workspace too small for host staging");
+  char* ws = (char*)workspace;
+  std::vector<const void*> dev_inputs(p->n_inputs);
+  for (int i = 0; i < p->n_inputs; ++i) {
+    CUDA_TRY(cudaMemcpyAsync(ws + in_off[i], host_inputs[i], (size_t)input_nbytes[i], cudaMemcpyHostToDevice, st));
+    dev_inputs[i] = ws + in_off[i];
+  }
+  CUDA_TRY(cudaMemsetAsync(ws + out_off, 0, (size_t)p->out_elements * es, st));
+  double* d_exp = (double*)(ws + exp_off);
+  if (p->strip_exponent) {
+    // running exponent starts at -inf so that the first slice sets it
+    const double ninf = -__builtin_huge_val();
+    CUDA_TRY(cudaMemcpyAsync(d_exp, &ninf, sizeof(double), cudaMemcpyHostToDevice, st));
+  }
+  int rc = ctgb_plan_execute(p, dev_inputs.data(), ws + out_off, d_exp, workspace, core, slice_begin, slice_step,
+                             slice_count, stream);
+  if (rc) return rc;
+  CUDA_TRY(cudaMemcpyAsync(host_out, ws + out_off, (size_t)p->out_elements * es, cudaMemcpyDeviceToHost, st));
+  if (p->strip_exponent && host_exponent)
+    CUDA_TRY(cudaMemcpyAsync(host_exponent, d_exp, sizeof(double), cudaMemcpyDeviceToHost, st));
+  CUDA_TRY(cudaStreamSynchronize(st));
+  return CTGB_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,166 @@
+"""Host-side lowering (classification, coalescing, tiling, descriptor packing)
+checked on the CPU through ``tests/desc_emulator.py`` against the golden values
+of the unmodified reference and against numpy.einsum."""
+
+import numpy as np
+import pytest
+
+from cotengra_b200 import lowering as L
+from tests.desc_emulator import emulate_pair, emulate_single
+from tests.helpers import load_json, load_npz, make_arrays, rel_err
+
+PARSERS = load_json("parsers.json")
+PVALS = load_npz("parsers_values.npz")
+VARIANTS = [L.VAR_SIMT_64x64, L.VAR_DMMA_128x64, L.VAR_DMMA_64x128, L.VAR_DMMA_256x32]
+
+
+def run_pair(eq, a, b, variant=None, splitk=None, sm_count=148):
+    terms, out = L.split_equation(eq)
+    dims = L.classify_pair(terms[0], a.shape, terms[1], b.shape, out)
+    n_out = int(np.prod(dims.out_shape)) if dims.out_shape else 1
+    plan = L.build_pair_desc(dims, str(a.dtype), sm_count=sm_count, variant=variant,
+                             c_dense_elems=n_out, force_splitk=splitk)
+    C = np.full(max(n_out, 1), np.nan, dtype=a.dtype)
+    A, B = a.reshape(-1), b.reshape(-1)
+    if plan.swapped:
+        A, B = B, A
+    if n_out:
+        emulate_pair(plan.words, A, B, C)
+    return C[:n_out].reshape(dims.out_shape), plan
+
+
+def test_golden_pair_cases_all_variants():
+    checked = 0
+    for n, rec in enumerate(PARSERS["pair"]):
+        sa, sb = tuple(rec["shape_a"]), tuple(rec["shape_b"])
+        terms, out = L.split_equation(rec["eq"])
+        if "error" in rec:
+            with pytest.raises(ValueError):
+                L.classify_pair(terms[0], sa, terms[1], sb, out)
+            continue
+        key = f"pair_{n}"
+        if key not in PVALS:
+            continue
+        a, b = make_arrays([sa, sb], "complex128", seed=n)
+        variant = VARIANTS[n % len(VARIANTS)]
+        got, _ = run_pair(rec["eq"], a, b, variant=variant)
+        want = PVALS[key]
+        assert got.shape == want.shape, rec
+        assert rel_err(got, want) < 1e-12, (rec, variant)
+        checked += 1
+    assert checked > 300
+
+
+def _rand_eq(rng, dmax=7):
+    letters = "abcdefghijkl"
+    n_ix = int(rng.integers(2, 9))
+    pool = list(rng.choice(list(letters), n_ix, replace=False))
+    sizes = {c: int(rng.integers(1, dmax + 1)) for c in pool}
+    ta = list(rng.permutation(pool)[: rng.integers(1, min(6, n_ix) + 1)])
+    tb = list(rng.permutation(pool)[: rng.integers(1, min(6, n_ix) + 1)])
+    present = list(dict.fromkeys(ta + tb))
+    out = [c for c in present if rng.random() < 0.55]
+    out = list(rng.permutation(out)) if out else []
+    eq = f"{''.join(ta)},{''.join(tb)}->{''.join(out)}"
+    return eq, tuple(sizes[c] for c in ta), tuple(sizes[c] for c in tb)
+
+
+@pytest.mark.parametrize("seed", range(6))
+def test_random_equations_vs_numpy(seed):
+    rng = np.random.default_rng(seed)
+    for trial in range(25):
+        eq, sa, sb = _rand_eq(rng)
+        a, b = make_arrays([sa, sb], "float64", seed=seed * 100 + trial)
+        want = np.einsum(eq, a, b)
+        for variant in (None, VARIANTS[trial % len(VARIANTS)]):
+            for splitk in (None, 3):
+                got, plan = run_pair(eq, a, b, variant=variant, splitk=splitk, sm_count=4)
+                assert got.shape == want.shape
+                assert rel_err(got, want) < 1e-12, (eq, sa, sb, variant, splitk)
+
+
+def test_partial_tiles_and_large_dims():
+    # extents that do not divide the tile: ragged last blocks in m, n and k
+    for (m, n, k) in [(130, 70, 19), (257, 3, 33), (5, 300, 9), (64, 64, 8), (1, 1, 2500)]:
+        a, b = make_arrays([(m, k), (k, n)], "complex128", seed=m + n + k)
+        want = a @ b
+        for variant in VARIANTS:
+            got, plan = run_pair("ab,bc->ac", a, b, variant=variant)
+            assert rel_err(got, want) < 1e-12, (m, n, k, variant)
+    # dot product goes to the k-reduction variant with split-K
+    a, b = make_arrays([(40, 300), (300, 40)], "complex128", seed=3)
+    got, plan = run_pair("ab,ba->", a, b)
+    assert plan.variant == L.VAR_KRED and plan.splitk > 1
+    assert rel_err(got, np.einsum("ab,ba->", a, b)) < 1e-12
+
+
+def test_rank30_permuted_operand_coalesces():
+    # Sycamore-like: all dims 2, scattered contracted indices
+    rng = np.random.default_rng(0)
+    ixs = [chr(ord("a") + i) for i in range(14)]
+    ta = list(rng.permutation(ixs))
+    con = list(rng.choice(ixs, 4, replace=False))
+    extra = ["A", "B", "C"]
+    tb = list(rng.permutation(con + extra))
+    out = [c for c in ta if c not in con] + [c for c in tb if c not in con]
+    eq = f"{''.join(ta)},{''.join(tb)}->{''.join(out)}"
+    a, b = make_arrays([(2,) * len(ta), (2,) * len(tb)], "complex128", seed=1)
+    want = np.einsum(eq, a, b)
+    for variant in VARIANTS:
+        got, plan = run_pair(eq, a, b, variant=variant)
+        assert rel_err(got, want) < 1e-12
+
+
+def test_tensordot_terms_match_numpy():
+    rng = np.random.default_rng(4)
+    for trial in range(60):
+        na, nb = int(rng.integers(0, 5)), int(rng.integers(0, 5))
+        nc = int(rng.integers(0, min(na, nb) + 1))
+        ax_a = tuple(int(x) for x in rng.choice(na, nc, replace=False)) if nc else ()
+        ax_b = tuple(int(x) for x in rng.choice(nb, nc, replace=False)) if nc else ()
+        sa = [int(rng.integers(1, 4)) for _ in range(na)]
+        sb = [int(rng.integers(1, 4)) for _ in range(nb)]
+        for i, j in zip(ax_a, ax_b):
+            sb[j] = sa[i]
+        a, b = make_arrays([sa, sb], "float64", seed=trial)
+        want = np.tensordot(a, b, (ax_a, ax_b))
+        perm = tuple(int(x) for x in rng.permutation(want.ndim)) if want.ndim else None
+        ta, tb, to = L.tensordot_terms((ax_a, ax_b), na, nb, perm)
+        dims = L.classify_pair(ta, a.shape, tb, b.shape, to)
+        plan = L.build_pair_desc(dims, "float64", c_dense_elems=max(want.size, 1))
+        C = np.zeros(max(want.size, 1))
+        A, B = (b.reshape(-1), a.reshape(-1)) if plan.swapped else (a.reshape(-1), b.reshape(-1))
+        emulate_pair(plan.words, A, B, C)
+        if perm is not None:
+            want = np.transpose(want, perm)
+        assert dims.out_shape == want.shape
+        assert rel_err(C[: want.size].reshape(want.shape), want) < 1e-12
+    with pytest.raises(ValueError):
+        L.check_tensordot_shapes(((0,), (0,)), (2, 3), (3, 2))
+    with pytest.raises(ValueError):
+        L.tensordot_terms(((0, 1), (0,)), 2, 2)
+
+
+def test_single_operand_cases():
+    for n, rec in enumerate(PARSERS["single"]):
+        shape = tuple(rec["shape"])
+        (x,) = make_arrays([shape], "complex128", seed=1000 + n)
+        terms, out = L.split_equation(rec["eq"])
+        odims, sdims, oshape = L.classify_single(terms[0], shape, out)
+        W = L.build_single_desc(odims, sdims, "complex128")
+        want = PVALS[f"single_{n}"]
+        res = np.zeros(max(want.size, 1), dtype=np.complex128)
+        emulate_single(W, x.reshape(-1), res)
+        assert tuple(oshape) == want.shape
+        assert rel_err(res[: want.size].reshape(want.shape), want) < 1e-12, rec
+
+
+def test_errors_match_reference():
+    with pytest.raises(ValueError):
+        L.classify_pair("ab", (2, 3), "bc", (4, 2), "ac")  # mismatched b
+    with pytest.raises(ValueError):
+        L.classify_pair("ab", (2,), "bc", (2, 2), "ac")  # term vs shape
+    with pytest.raises(NotImplementedError):
+        L.split_equation("a...,b->")
+    with pytest.raises(TypeError):
+        L.dtype_name("int32")

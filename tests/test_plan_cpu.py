@@ -1,0 +1,83 @@
+"""``ExecPlan`` (arenas, slice offsets, invariant hoisting, root views,
+exponent stripping) emulated on the CPU against the reference's golden values."""
+
+import numpy as np
+import pytest
+
+from cotengra_b200 import ExecPlan, TreeSpec
+from tests.desc_emulator import emulate_plan
+from tests.helpers import decode_ir, decode_sliced, load_json, load_npz, make_arrays, rel_err
+
+TREES = load_json("trees.json")
+TVALS = load_npz("trees_values.npz")
+
+
+def _plan(rec, ir=None, **kw):
+    n_in = len(rec["inputs"])
+    node_inds = {int(k): v for k, v in rec["inds"].items() if int(k) >= n_in}
+    spec = TreeSpec(rec["inputs"], rec["output"], rec["size_dict"], rec["path"],
+                    decode_sliced(rec["sliced"]), node_inds)
+    ir = spec.contractions() if ir is None else ir
+    return spec, ExecPlan(ir, spec.inputs, spec.output, spec.size_dict, spec.sliced,
+                          dtype=rec["dtype"], sm_count=8, **kw)
+
+
+@pytest.mark.parametrize("rec", TREES, ids=[r["name"] for r in TREES])
+def test_plan_values(rec):
+    if rec["name"] not in TVALS:
+        pytest.skip("no full value recorded")
+    spec, plan = _plan(rec)
+    arrays = make_arrays(spec.shapes(), rec["dtype"], seed=rec["seed"])
+    want = TVALS[rec["name"]]
+    got = emulate_plan(plan, arrays)
+    assert got.shape == want.shape
+    assert rel_err(got, want) < 1e-11
+    # the reference's own IR (from the golden file) gives the same plan result
+    _, plan2 = _plan(rec, ir=decode_ir(rec["contractions"]), hoist=False)
+    assert rel_err(emulate_plan(plan2, arrays), want) < 1e-11
+    if rec["strip_exponent"]:
+        _, plan3 = _plan(rec, strip_exponent=True)
+        m, e = emulate_plan(plan3, arrays)
+        assert rel_err(m * 10.0**e, want) < 1e-10
+        # same (mantissa, exponent) normalisation as gather_slices: max|m| <= 1 scale
+        wm, we = TVALS[rec["name"] + "_m"], float(TVALS[rec["name"] + "_e"])
+        assert rel_err(m * 10.0 ** (e - we), wm) < 1e-10
+
+
+def test_single_slices_and_round_robin():
+    rec = next(r for r in TREES if r["name"] == "lattice6x6_d3_sliced")
+    spec, plan = _plan(rec)
+    arrays = make_arrays(spec.shapes(), rec["dtype"], seed=rec["seed"])
+    for i in list(rec["slice_keys"])[:3]:
+        got = emulate_plan(plan, arrays, slice_ids=[int(i)])
+        assert rel_err(got, TVALS[f"{rec['name']}_slice{i}"]) < 1e-11
+    # rank-strided partial sums add up to the full result (core.py:4070)
+    world = 3
+    parts = [emulate_plan(plan, arrays, slice_ids=range(r, plan.nslices, world)) for r in range(world)]
+    assert rel_err(sum(parts), TVALS[rec["name"]]) < 1e-11
+
+
+def test_hoisting_marks_invariant_nodes():
+    rec = next(r for r in load_json("sycamore_m20.json") if r["name"] == "sycamore_m20_appxB")
+    spec, plan = _plan(rec)
+    inv = sum(1 for nd in plan.nodes if nd["invariant"])
+    assert inv == 195  # 195 of 380 nodes are slice-invariant
+    assert plan.macs_per_slice + plan.macs_invariant == rec["contraction_cost"] // rec["nslices"]
+    assert plan.nslices == 2**36
+    # peak live memory stays near the reference's tree.peak_size()
+    assert plan.workspace_bytes <= 1.25 * rec["peak_size"] * plan.esize
+
+
+def test_arena_never_overlaps_live_tensors():
+    rec = next(r for r in TREES if r["name"] == "peps8x8_d2")
+    spec, plan = _plan(rec)
+    live = {}
+    for nd in plan.nodes:
+        c = nd["c"]
+        if c.kind == 1:
+            for other in live.values():
+                assert c.offset + c.nbytes <= other.offset or other.offset + other.nbytes <= c.offset
+            live[id(c)] = c
+        for s in (nd["a"], nd["b"]):
+            if s is not None and s.kind == 1 and s.last_use == nd["pos"]:
+                live.pop(id(s), None)
