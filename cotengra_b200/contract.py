@@ -61,7 +61,7 @@ def _to_device(x, device=None):
         if not x.is_cuda:
             x = x.cuda(device)
         return x.contiguous(), False
-    x = np.ascontiguousarray(x)
+    x = np.asarray(x, order="C")  # (ascontiguousarray would promote 0-d to 1-d)
     dtype_name(x.dtype)
     return torch.from_numpy(x).cuda(device), True
 
@@ -244,7 +244,7 @@ class TreeExecutor:
         self._check_inputs(arrays)
         if count is None:
             count = max(0, -(-(self.nslices - begin) // step))
-        host = [np.ascontiguousarray(a, dtype=self.dtype) for a in arrays]
+        host = [np.asarray(a, dtype=self.dtype, order="C") for a in arrays]
         out = np.zeros(self.plan.out_shape, dtype=self.dtype)
         with torch.cuda.device(self.device):
             ws = self.workspace(host_staging=True)

@@ -119,6 +119,7 @@ int launch_gett_typed(const int64_t* h, const int64_t* d, const void* A, const v
   switch (variant) {
     case VAR_SIMT_64x64: return launch_gett_policy<T, SimtPolicy<T, 64, 64, 8, 3>>(h, d, A, B, C, st);
     case VAR_KRED: return launch_gett_policy<T, KredPolicy<T, 1, 1, 1024, 3>>(h, d, A, B, C, st);
+    case VAR_ROW_128x8: return launch_gett_policy<T, RowPolicy<T, 128, 8, 8, 2>>(h, d, A, B, C, st);
     default: break;
   }
   if constexpr (sizeof(T) == 16 || (sizeof(T) == 8 && std::is_same<T, double>::value)) {
@@ -126,6 +127,7 @@ int launch_gett_typed(const int64_t* h, const int64_t* d, const void* A, const v
       case VAR_DMMA_128x64: return launch_gett_policy<T, DmmaPolicy<T, 4, 2, 4, 4, 16, 3>>(h, d, A, B, C, st);
       case VAR_DMMA_64x128: return launch_gett_policy<T, DmmaPolicy<T, 2, 4, 4, 4, 16, 3>>(h, d, A, B, C, st);
       case VAR_DMMA_256x32: return launch_gett_policy<T, DmmaPolicy<T, 8, 1, 4, 4, 8, 3>>(h, d, A, B, C, st);
+      case VAR_DMMA_256x16: return launch_gett_policy<T, DmmaPolicy<T, 8, 1, 4, 2, 8, 2>>(h, d, A, B, C, st);
       default: break;
     }
   }
@@ -362,7 +364,7 @@ int ctgb_plan_create(const ctgb_plan_desc* pd, ctgb_plan** out) {
     q.c = n.c;
     q.invariant = n.invariant;
     q.is_root = n.is_root;
-    const int words = n.kind == 0 ? DESC_WORDS : SDESC_WORDS;
+    const int words = n.kind == 0 ? (int)DESC_WORDS : (int)SDESC_WORDS;
     const int64_t magic = n.kind == 0 ? DESC_MAGIC : SDESC_MAGIC;
     if (!n.desc || n.desc[0] != magic) {
       delete p;
@@ -536,15 +538,16 @@ int ctgb_plan_execute(ctgb_plan* p, const void* const* inputs, void* out, double
     // slice id -> digits, most significant first (core.py:3775-3800)
     int64_t i = slice_begin + k * slice_step;
     {
+      // least-significant digit first: the same digits as i // stride_j % radix_j,
+      // without forming the strides (their product overflows 64 bits for trees
+      // with more than 63 binary sliced indices; ids themselves are < 2^63)
       int64_t rem = i;
-      std::vector<int64_t> strides(ns, 1);
-      for (int j = ns - 2; j >= 0; --j) strides[j] = strides[j + 1] * p->radix[j + 1];
-      for (int j = 0; j < ns; ++j) {
+      for (int j = ns - 1; j >= 0; --j) {
         if (p->project[j] >= 0) {
           digits[j] = p->project[j];
         } else {
-          digits[j] = rem / strides[j];
-          rem %= strides[j];
+          digits[j] = rem % p->radix[j];
+          rem /= p->radix[j];
         }
       }
     }

@@ -62,8 +62,8 @@ enum : int {
   VAR_DMMA_128x64 = 2, // fp64 tensor-core (mma.sync m8n8k4) tile kernel
   VAR_DMMA_64x128 = 3,
   VAR_DMMA_256x32 = 4,
-  VAR_DMMA_512x16 = 5,
-  VAR_DMMA_1024x8 = 6
+  VAR_DMMA_256x16 = 5,
+  VAR_ROW_128x8 = 6    // one output row per thread (HBM-bound skinny nodes)
 };
 
 // ---- single-operand descriptor (cotengra/contract.py:332-361) -------------

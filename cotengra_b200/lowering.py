@@ -57,6 +57,7 @@ SDESC_WORDS = OFF_SS + MAX_S * 2
 SDESC_MAGIC = 0x4354474253303031
 
 VAR_SIMT_64x64, VAR_KRED, VAR_DMMA_128x64, VAR_DMMA_64x128, VAR_DMMA_256x32 = 0, 1, 2, 3, 4
+VAR_DMMA_256x16, VAR_ROW_128x8 = 5, 6
 # (MT, NT, KT) of every kernel variant -- must match ctg_b200.cu's dispatch
 VARIANT_TILES = {
     VAR_SIMT_64x64: (64, 64, 8),
@@ -64,6 +65,8 @@ VARIANT_TILES = {
     VAR_DMMA_128x64: (128, 64, 16),
     VAR_DMMA_64x128: (64, 128, 16),
     VAR_DMMA_256x32: (256, 32, 8),
+    VAR_DMMA_256x16: (256, 16, 8),
+    VAR_ROW_128x8: (128, 8, 8),
 }
 
 DTYPE_CODES = {"float32": 0, "float64": 1, "complex64": 2, "complex128": 3}
@@ -71,8 +74,12 @@ DTYPE_SIZES = {"float32": 4, "float64": 8, "complex64": 8, "complex128": 16}
 
 
 def dtype_name(dtype) -> str:
-    name = str(np.dtype(dtype)) if not isinstance(dtype, str) else dtype
-    name = name.replace("torch.", "")
+    if isinstance(dtype, str):
+        name = dtype
+    elif str(dtype).startswith("torch."):
+        name = str(dtype)[len("torch."):]
+    else:
+        name = str(np.dtype(dtype))
     if name not in DTYPE_CODES:
         raise TypeError(f"unsupported dtype {dtype!r}")
     return name
@@ -309,12 +316,16 @@ class PairPlan:
 def choose_variant(dtype, B, M, N, K, allow_dmma=True):
     if M == 1 and N == 1 and B == 1 and K >= 8192:
         return VAR_KRED
+    if N <= 8 and M >= 64:
+        return VAR_ROW_128x8
     if allow_dmma and dtype in ("float64", "complex128") and M * N * K >= 1 << 15 and M * N >= 1024:
         if N >= 96:
             return VAR_DMMA_64x128
         if N >= 48:
             return VAR_DMMA_128x64
-        return VAR_DMMA_256x32
+        if N >= 24:
+            return VAR_DMMA_256x32
+        return VAR_DMMA_256x16
     return VAR_SIMT_64x64
 
 
@@ -407,7 +418,21 @@ def build_pair_desc(dims: PairDims, dtype, accumulate=False, sm_count=148,
         else:
             W[base:base + 4] = p
     W[W_NLDA], W[W_NLDB] = len(lda), len(ldb)
-    W[W_FLAGS] = 1 if accumulate else 0
+    # bit1: columns (2q, 2q+1) of every tile row are adjacent in C and 32-byte
+    # aligned -> the kernels may use 256-bit stores (complex128 only)
+    expected, dense_n = 1, True
+    for d in tn:
+        if d[2] != expected:
+            dense_n = False
+            break
+        expected *= d[0]
+    pair_ok = (
+        dtype == "complex128" and dense_n and pn is None and NTa >= 2 and NTa % 2 == 0
+        and all(d[2] % 2 == 0 for d in tm)
+        and all(g[3] % 2 == 0 for g in gm) and all(g[3] % 2 == 0 for g in gn)
+        and all(g[4] % 2 == 0 for g in gb)
+    )
+    W[W_FLAGS] = (1 if accumulate else 0) | (2 if pair_ok else 0)
     W[W_VARIANT] = variant
     W[W_CELEMS] = int(c_dense_elems)
 

@@ -36,7 +36,7 @@ def _cast(x, dtype):
     dtype = np.dtype(dtype)
     if dtype.kind != "c":
         x = np.real(x)
-    return np.ascontiguousarray(x).astype(dtype)
+    return np.asarray(x, order="C").astype(dtype)
 
 
 def test_native_library_is_loaded_and_launches():
@@ -105,7 +105,7 @@ def test_tensordot_golden_shapes():
 
 
 @pytest.mark.parametrize("variant", [L.VAR_SIMT_64x64, L.VAR_DMMA_128x64, L.VAR_DMMA_64x128,
-                                     L.VAR_DMMA_256x32])
+                                     L.VAR_DMMA_256x32, L.VAR_DMMA_256x16, L.VAR_ROW_128x8])
 @pytest.mark.parametrize("dtype", ["complex128", "float64"])
 def test_every_kernel_variant_ragged_gemm(variant, dtype):
     import torch
@@ -133,8 +133,8 @@ def test_equations_through_contractor():
         arrays = make_arrays(rec["shapes"], "complex128", seed=rec["seed"])
         n = len(arrays)
         # a left-to-right chain tree over the operands of the equation
-        lhs, out = rec["eq"].split("->")
-        inputs = [tuple(t) for t in lhs.split(",")]
+        terms, out = L.split_equation(rec["eq"])
+        inputs = [tuple(t) for t in terms]
         size_dict = {}
         for t, s in zip(inputs, rec["shapes"]):
             for ix, d in zip(t, s):
