@@ -95,7 +95,7 @@ int launch_gett_policy(const int64_t* h, const int64_t* d, const void* A, const 
   }
   static thread_local int occ = 0;
   if (occ == 0) {
-    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, gett_kernel<T, P>, P::THREADS, smem));
+    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, gett_kernel<T, P>, P::THREADS + PRODUCER_THREADS, smem));
     if (occ < 1) occ = 1;
   }
   const uint64_t work = (uint64_t)h[W_TILES_M] * (uint64_t)h[W_TILES_N] * (uint64_t)h[W_TILES_B] * (uint64_t)h[W_SPLITK];
@@ -107,7 +107,7 @@ int launch_gett_policy(const int64_t* h, const int64_t* d, const void* A, const 
     if (h[W_CELEMS] <= 0) return fail(CTGB_E_VALUE, "split-K into a strided C needs accumulate");
     CUDA_TRY(cudaMemsetAsync(C, 0, (size_t)h[W_CELEMS] * sizeof(T), st));
   }
-  gett_kernel<T, P><<<(unsigned)grid, P::THREADS, smem, st>>>(d, (const T*)A, (const T*)B, (T*)C);
+  gett_kernel<T, P><<<(unsigned)grid, P::THREADS + PRODUCER_THREADS, smem, st>>>(d, (const T*)A, (const T*)B, (T*)C);
   g_launches.fetch_add(1, std::memory_order_relaxed);
   CUDA_TRY(cudaGetLastError());
   return CTGB_OK;
@@ -119,7 +119,7 @@ int launch_gett_typed(const int64_t* h, const int64_t* d, const void* A, const v
   switch (variant) {
     case VAR_SIMT_64x64: return launch_gett_policy<T, SimtPolicy<T, 64, 64, 8, 3>>(h, d, A, B, C, st);
     case VAR_KRED: return launch_gett_policy<T, KredPolicy<T, 1, 1, 1024, 3>>(h, d, A, B, C, st);
-    case VAR_ROW_128x8: return launch_gett_policy<T, RowPolicy<T, 128, 8, 8, 2>>(h, d, A, B, C, st);
+    case VAR_ROW_128x8: return launch_gett_policy<T, RowPolicy<T, 256, 8, 8, 2>>(h, d, A, B, C, st);
     default: break;
   }
   if constexpr (sizeof(T) == 16 || (sizeof(T) == 8 && std::is_same<T, double>::value)) {
@@ -127,7 +127,7 @@ int launch_gett_typed(const int64_t* h, const int64_t* d, const void* A, const v
       case VAR_DMMA_128x64: return launch_gett_policy<T, DmmaPolicy<T, 4, 2, 4, 4, 16, 3>>(h, d, A, B, C, st);
       case VAR_DMMA_64x128: return launch_gett_policy<T, DmmaPolicy<T, 2, 4, 4, 4, 16, 3>>(h, d, A, B, C, st);
       case VAR_DMMA_256x32: return launch_gett_policy<T, DmmaPolicy<T, 8, 1, 4, 4, 8, 3>>(h, d, A, B, C, st);
-      case VAR_DMMA_256x16: return launch_gett_policy<T, DmmaPolicy<T, 8, 1, 4, 2, 8, 2>>(h, d, A, B, C, st);
+      case VAR_DMMA_256x16: return launch_gett_policy<T, DmmaPolicy<T, 8, 1, 4, 2, 8, 3>>(h, d, A, B, C, st);
       default: break;
     }
   }

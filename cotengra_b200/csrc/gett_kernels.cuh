@@ -121,7 +121,8 @@ struct SimtPolicy {
   static constexpr int TM = MT / 16, TN = NT / 16;
   static constexpr int A_ELEMS = MT * KT, B_ELEMS = NT * KT;
   static constexpr int SCRATCH_ELEMS = 0;
-  static constexpr int MIN_BLOCKS = 2;
+  static constexpr int CONSUMER_REGS = 0, PRODUCER_REGS = 0;
+  static constexpr int MIN_BLOCKS = sizeof(T) == 16 ? 1 : 2;
   struct Acc {
     T v[TM][TN];
   };
@@ -134,7 +135,7 @@ struct SimtPolicy {
       for (int j = 0; j < TN; ++j) acc.v[i][j] = zero_of<T>();
   }
   __device__ static __forceinline__ void compute(const T* __restrict__ sA, const T* __restrict__ sB, Acc& acc,
-                                                 int kvalid) {
+                                                 int kvalid, int ncols) {
     const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
 #pragma unroll
     for (int kk = 0; kk < KT; ++kk) {
@@ -150,7 +151,8 @@ struct SimtPolicy {
     }
   }
   template <typename F, typename F2>
-  __device__ static __forceinline__ void epilogue(Acc& acc, T* scratch, F&& store, F2&& store_pair, bool pair_ok) {
+  __device__ static __forceinline__ void epilogue(Acc& acc, T* scratch, F&& store, F2&& store_pair, bool pair_ok,
+                                                  int ncols) {
     const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
 #pragma unroll
     for (int i = 0; i < TM; ++i)
@@ -168,6 +170,7 @@ struct KredPolicy {
   static constexpr int THREADS = 256;
   static constexpr int A_ELEMS = MT * KT, B_ELEMS = NT * KT;
   static constexpr int SCRATCH_ELEMS = MT * NT * (THREADS / 32);
+  static constexpr int CONSUMER_REGS = 0, PRODUCER_REGS = 0;
   static constexpr int MIN_BLOCKS = 1;
   struct Acc {
     T v[MT][NT];
@@ -181,7 +184,7 @@ struct KredPolicy {
       for (int j = 0; j < NT; ++j) acc.v[i][j] = zero_of<T>();
   }
   __device__ static __forceinline__ void compute(const T* __restrict__ sA, const T* __restrict__ sB, Acc& acc,
-                                                 int kvalid) {
+                                                 int kvalid, int ncols) {
 #pragma unroll
     for (int kk = threadIdx.x; kk < KT; kk += THREADS) {
       T a[MT], b[NT];
@@ -196,7 +199,8 @@ struct KredPolicy {
     }
   }
   template <typename F, typename F2>
-  __device__ static __forceinline__ void epilogue(Acc& acc, T* scratch, F&& store, F2&& store_pair, bool pair_ok) {
+  __device__ static __forceinline__ void epilogue(Acc& acc, T* scratch, F&& store, F2&& store_pair, bool pair_ok,
+                                                  int ncols) {
     // block reduction of every (r, c) partial sum: shuffles, then 8 warps via smem
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 #pragma unroll
@@ -208,14 +212,14 @@ struct KredPolicy {
         for (int d = 16; d > 0; d >>= 1) v = add_of(v, shfl_down_of(v, d));
         if (lane == 0) scratch[(i * NT + j) * (THREADS / 32) + warp] = v;
       }
-    __syncthreads();
+    asm volatile("bar.sync 2, %0;\n" ::"n"(THREADS) : "memory");  // consumers only
     if (threadIdx.x < MT * NT) {
       T v = zero_of<T>();
 #pragma unroll
       for (int w = 0; w < THREADS / 32; ++w) v = add_of(v, scratch[threadIdx.x * (THREADS / 32) + w]);
       store(threadIdx.x / NT, threadIdx.x % NT, v);
     }
-    __syncthreads();
+    asm volatile("bar.sync 2, %0;\n" ::"n"(THREADS) : "memory");
   }
 };
 
@@ -228,7 +232,8 @@ struct RowPolicy {
   static constexpr int THREADS = MT;
   static constexpr int A_ELEMS = MT * KT, B_ELEMS = NT * KT;
   static constexpr int SCRATCH_ELEMS = 0;
-  static constexpr int MIN_BLOCKS = 4;
+  static constexpr int CONSUMER_REGS = 0, PRODUCER_REGS = 0;
+  static constexpr int MIN_BLOCKS = 2;
   struct Acc {
     T v[NT];
   };
@@ -239,24 +244,34 @@ struct RowPolicy {
     for (int j = 0; j < NT; ++j) acc.v[j] = zero_of<T>();
   }
   __device__ static __forceinline__ void compute(const T* __restrict__ sA, const T* __restrict__ sB, Acc& acc,
-                                                 int kvalid) {
-#pragma unroll
+                                                 int kvalid, int ncols) {
+#pragma unroll 1
     for (int kk = 0; kk < KT; ++kk) {
       if (kk >= kvalid) break;
       const T a = sA[kk * MT + threadIdx.x];
 #pragma unroll
-      for (int j = 0; j < NT; ++j) mac(acc.v[j], a, sB[kk * NT + j]);
+      for (int j = 0; j < NT; ++j) {
+        if (j >= ncols) break;
+        mac(acc.v[j], a, sB[kk * NT + j]);
+      }
     }
   }
   template <typename F, typename F2>
-  __device__ static __forceinline__ void epilogue(Acc& acc, T* scratch, F&& store, F2&& store_pair, bool pair_ok) {
+  __device__ static __forceinline__ void epilogue(Acc& acc, T* scratch, F&& store, F2&& store_pair, bool pair_ok,
+                                                  int ncols) {
     if (pair_ok) {
       // the row's columns are adjacent in C: 32-byte (256-bit) stores, full sectors
 #pragma unroll
-      for (int j = 0; j < NT; j += 2) store_pair((int)threadIdx.x, j, acc.v[j], acc.v[j + 1]);
+      for (int j = 0; j < NT; j += 2) {
+        if (j >= ncols) break;
+        store_pair((int)threadIdx.x, j, acc.v[j], acc.v[j + 1]);
+      }
     } else {
 #pragma unroll
-      for (int j = 0; j < NT; ++j) store((int)threadIdx.x, j, acc.v[j]);
+      for (int j = 0; j < NT; ++j) {
+        if (j >= ncols) break;
+        store((int)threadIdx.x, j, acc.v[j]);
+      }
     }
   }
 };
@@ -280,6 +295,8 @@ struct DmmaPolicy {
   static constexpr int THREADS = WARPS_M * WARPS_N * 32;
   static constexpr int A_ELEMS = MT * KT, B_ELEMS = NT * KT;
   static constexpr int SCRATCH_ELEMS = 0;
+  // 8 consumer warps x 232 + 4 producer warps x 40 registers = 64512 <= 65536
+  static constexpr int CONSUMER_REGS = (THREADS == 256) ? 232 : 0, PRODUCER_REGS = 40;
   static constexpr int MIN_BLOCKS = 1;
   static_assert(KT % 4 == 0, "KT must be a multiple of the DMMA k");
   struct Acc {
@@ -300,7 +317,7 @@ struct DmmaPolicy {
       }
   }
   __device__ static __forceinline__ void compute(const T* __restrict__ sA, const T* __restrict__ sB, Acc& acc,
-                                                 int kvalid) {
+                                                 int kvalid, int ncols) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int wm = warp % WARPS_M, wn = warp / WARPS_M;
     const int frow = lane >> 2, fk = lane & 3;
@@ -346,7 +363,8 @@ struct DmmaPolicy {
     }
   }
   template <typename F, typename F2>
-  __device__ static __forceinline__ void epilogue(Acc& acc, T* scratch, F&& store, F2&& store_pair, bool pair_ok) {
+  __device__ static __forceinline__ void epilogue(Acc& acc, T* scratch, F&& store, F2&& store_pair, bool pair_ok,
+                                                  int ncols) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int wm = warp % WARPS_M, wn = warp / WARPS_M;
     const int frow = lane >> 2, fc = (lane & 3) * 2;
@@ -373,360 +391,7 @@ struct DmmaPolicy {
   }
 };
 
-// ------------------------------------------------------------------ skeleton
-constexpr int KCHUNK = 128;  // k-steps whose base offsets are tabulated once per kernel
-
-template <class P>
-struct GettSmem {
-  static constexpr int NA = (P::A_ELEMS + P::THREADS - 1) / P::THREADS;
-  static constexpr int NB = (P::B_ELEMS + P::THREADS - 1) / P::THREADS;
-  static constexpr int TI = P::STAGES + 1;  // tile-info ring
-  template <typename T>
-  static constexpr size_t bytes() {
-    return sizeof(T) * ((size_t)P::STAGES * (P::A_ELEMS + P::B_ELEMS) + P::SCRATCH_ELEMS)  // ring + scratch
-           + 8 * (size_t)(NA + NB) * P::THREADS                                            // element deltas
-           + 8 * (size_t)(P::MT + P::NT)                                                   // C offsets
-           + 8 * (size_t)2 * KCHUNK                                                        // k-step bases
-           + 8 * (size_t)3 * TI                                                            // tile bases
-           + 4 * (size_t)(NA + NB) * P::THREADS                                            // element (r, kk)
-           + 4 * (size_t)KCHUNK + 4 * (size_t)2 * TI + 4 * (size_t)P::STAGES               // valid counts
-           + 64;
-  }
-};
-
-// One CTA walks its work items (tile x k-split) as ONE stream of k-steps: the
-// cp.async ring keeps prefetching across tile boundaries, so tiles with few
-// k-steps (K <= 64 on Sycamore trees) and single-step HBM-bound tiles never
-// drain the pipeline.
-template <typename T, class P>
-__global__ void __launch_bounds__(P::THREADS, P::MIN_BLOCKS)
-gett_kernel(const int64_t* __restrict__ D, const T* __restrict__ A, const T* __restrict__ B, T* __restrict__ C) {
-  constexpr int MT = P::MT, NT = P::NT, STAGES = P::STAGES, THREADS = P::THREADS;
-  constexpr int NA = GettSmem<P>::NA, NB = GettSmem<P>::NB, TI = GettSmem<P>::TI;
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  T* sA = reinterpret_cast<T*>(smem_raw);
-  T* sB = sA + STAGES * P::A_ELEMS;
-  T* scratch = sB + STAGES * P::B_ELEMS;
-  long long* gA = reinterpret_cast<long long*>(scratch + P::SCRATCH_ELEMS);
-  long long* gB = gA + NA * THREADS;
-  long long* offMC = gB + NB * THREADS;
-  long long* offNC = offMC + MT;
-  long long* kbA = offNC + NT;
-  long long* kbB = kbA + KCHUNK;
-  long long* ti_base = kbB + KCHUNK;  // [TI][3]: A, B, C
-  unsigned* metaA = reinterpret_cast<unsigned*>(ti_base + 3 * TI);
-  unsigned* metaB = metaA + NA * THREADS;
-  int* kval = reinterpret_cast<int*>(metaB + NB * THREADS);
-  int* ti_valid = kval + KCHUNK;       // [TI][2]: m_valid, n_valid
-  int* stage_kv = ti_valid + 2 * TI;   // [STAGES]
-
-  const int tid = threadIdx.x;
-  const int lane = tid & 31, warp = tid >> 5;
-
-  // ---- header (uniform loads through the read-only path) ----
-  const int n_tm = (int)D[W_NTM], n_tn = (int)D[W_NTN];
-  const int n_gm = (int)D[W_NGM], n_gn = (int)D[W_NGN], n_gk = (int)D[W_NGK], n_gb = (int)D[W_NGB];
-  const int MTa = (int)D[W_MTA], NTa = (int)D[W_NTA], KTa = (int)D[W_KTA];
-  const unsigned tiles_m = (unsigned)D[W_TILES_M], tiles_n = (unsigned)D[W_TILES_N], tiles_b = (unsigned)D[W_TILES_B];
-  const unsigned steps_k = (unsigned)D[W_STEPS_K], splitk = (unsigned)D[W_SPLITK];
-  const int pgm = (int)D[W_PGM], pgn = (int)D[W_PGN], pgk = (int)D[W_PGK];
-  const bool accumulate = (D[W_FLAGS] & 1) != 0;
-  const bool atomic = splitk > 1;
-  // bit1: every pair of columns (2q, 2q+1) is adjacent in C and 32-byte aligned
-  const bool pair_ok = (D[W_FLAGS] & 2) != 0 && !atomic && !accumulate && sizeof(T) == 16;
-  const bool ktab = steps_k <= (unsigned)KCHUNK;
-
-  // ---- one-time tables ----
-  // zero the operand ring: rows/cols/k beyond the actual tile are never loaded
-  for (int i = tid; i < STAGES * (P::A_ELEMS + P::B_ELEMS); i += THREADS) sA[i] = zero_of<T>();
-  // per-slot element tables, enumerated in operand-memory order for coalescing
-  {
-    const int n_lda = (int)D[W_NLDA], n_ldb = (int)D[W_NLDB];
-    for (int i = 0; i < NA; ++i) {
-      unsigned e = tid + i * THREADS;
-      long long g = 0;
-      unsigned r = 0, kk = 0xFFFFu;
-      if (e < (unsigned)(MTa * KTa)) {
-        kk = 0;
-        for (int d = 0; d < n_lda; ++d) {
-          const int64_t* L = D + OFF_LDA + d * 4;
-          unsigned ext = (unsigned)L[0];
-          unsigned dig = e % ext;
-          e /= ext;
-          g += (long long)dig * L[1];
-          r += dig * (unsigned)L[2];
-          kk += dig * (unsigned)L[3];
-        }
-      }
-      gA[i * THREADS + tid] = g;
-      metaA[i * THREADS + tid] = r | (kk << 16);
-    }
-    for (int i = 0; i < NB; ++i) {
-      unsigned e = tid + i * THREADS;
-      long long g = 0;
-      unsigned c = 0, kk = 0xFFFFu;
-      if (e < (unsigned)(NTa * KTa)) {
-        kk = 0;
-        for (int d = 0; d < n_ldb; ++d) {
-          const int64_t* L = D + OFF_LDB + d * 4;
-          unsigned ext = (unsigned)L[0];
-          unsigned dig = e % ext;
-          e /= ext;
-          g += (long long)dig * L[1];
-          kk += dig * (unsigned)L[2];
-          c += dig * (unsigned)L[3];
-        }
-      }
-      gB[i * THREADS + tid] = g;
-      metaB[i * THREADS + tid] = c | (kk << 16);
-    }
-  }
-  // local C offsets of every tile row / column
-  for (int r = tid; r < MT; r += THREADS) {
-    long long o = 0;
-    if (r < MTa) {
-      unsigned e = r;
-      for (int d = 0; d < n_tm; ++d) {
-        const int64_t* L = D + OFF_TM + d * 3;
-        unsigned ext = (unsigned)L[0];
-        o += (long long)(e % ext) * L[2];
-        e /= ext;
-      }
-    }
-    offMC[r] = o;
-  }
-  for (int c = tid; c < NT; c += THREADS) {
-    long long o = 0;
-    if (c < NTa) {
-      unsigned e = c;
-      for (int d = 0; d < n_tn; ++d) {
-        const int64_t* L = D + OFF_TN + d * 3;
-        unsigned ext = (unsigned)L[0];
-        o += (long long)(e % ext) * L[2];
-        e /= ext;
-      }
-    }
-    offNC[c] = o;
-  }
-  // k-step bases: a function of the absolute step index only
-  auto kstep_bases = [&](unsigned step, long long& a, long long& b, int& kv) {
-    a = 0;
-    b = 0;
-    kv = KTa;
-    for (int j = 0; j < n_gk; ++j) {
-      const int64_t* G = D + OFF_GK + j * 4;
-      unsigned dig = (step / (unsigned)G[1]) % (unsigned)G[0];
-      a += (long long)dig * G[2];
-      b += (long long)dig * G[3];
-      if (j == pgk)
-        kv = (int)min((long long)D[W_KTEXT], (long long)D[W_KFULL] - (long long)dig * (long long)D[W_KTEXT]) *
-             (int)D[W_KW];
-    }
-  };
-  if (ktab) {
-    for (unsigned s = tid; s < steps_k; s += THREADS) {
-      long long a, b;
-      int kv;
-      kstep_bases(s, a, b, kv);
-      kbA[s] = a;
-      kbB[s] = b;
-      kval[s] = kv;
-    }
-  }
-  __syncthreads();
-
-  // the host guarantees total_work < 2^31 (lowering.py)
-  const unsigned tiles_all = tiles_m * tiles_n * tiles_b;
-  const unsigned total_work = tiles_all * splitk;
-  const unsigned steps_per_split = (steps_k + splitk - 1) / splitk;
-  const unsigned nw = blockIdx.x < total_work ? (total_work - blockIdx.x + gridDim.x - 1) / gridDim.x : 0u;
-  if (nw == 0) return;
-
-  auto work_krange = [&](unsigned j, unsigned& k0, unsigned& k1) {
-    const unsigned w = blockIdx.x + j * gridDim.x;
-    const unsigned ks = w / tiles_all;
-    k0 = ks * steps_per_split;
-    k1 = min(steps_k, k0 + steps_per_split);
-  };
-
-  // grid-base offsets of work item j -> tile-info slot j % TI.  One warp, one
-  // lane per grid dim; n fastest so neighbouring CTAs share A tiles in L2.
-  auto decode_tile = [&](unsigned j) {
-    if (warp == 0) {
-      unsigned t = (blockIdx.x + j * gridDim.x) % tiles_all;
-      const unsigned in_ = t % tiles_n;
-      t /= tiles_n;
-      const unsigned im_ = t % tiles_m;
-      const unsigned ib_ = t / tiles_m;
-      long long a = 0, b = 0, c = 0;
-      int vm = 0, vn = 0;
-      for (int q = lane; q < n_gm; q += 32) {
-        const int64_t* G = D + OFF_GM + q * 4;
-        unsigned dig = (im_ / (unsigned)G[1]) % (unsigned)G[0];
-        a += (long long)dig * G[2];
-        c += (long long)dig * G[3];
-        if (q == pgm)
-          vm = (int)min((long long)D[W_MTEXT], (long long)D[W_MFULL] - (long long)dig * (long long)D[W_MTEXT]) *
-               (int)D[W_MW];
-      }
-      for (int q = lane; q < n_gn; q += 32) {
-        const int64_t* G = D + OFF_GN + q * 4;
-        unsigned dig = (in_ / (unsigned)G[1]) % (unsigned)G[0];
-        b += (long long)dig * G[2];
-        c += (long long)dig * G[3];
-        if (q == pgn)
-          vn = (int)min((long long)D[W_NTEXT], (long long)D[W_NFULL] - (long long)dig * (long long)D[W_NTEXT]) *
-               (int)D[W_NW];
-      }
-      for (int q = lane; q < n_gb; q += 32) {
-        const int64_t* G = D + OFF_GB + q * 5;
-        unsigned dig = (ib_ / (unsigned)G[1]) % (unsigned)G[0];
-        a += (long long)dig * G[2];
-        b += (long long)dig * G[3];
-        c += (long long)dig * G[4];
-      }
-      a = warp_sum_ll(a);
-      b = warp_sum_ll(b);
-      c = warp_sum_ll(c);
-      vm = warp_sum_i(vm);
-      vn = warp_sum_i(vn);
-      if (lane == 0) {
-        const int slot = (int)(j % TI);
-        ti_base[slot * 3 + 0] = a;
-        ti_base[slot * 3 + 1] = b;
-        ti_base[slot * 3 + 2] = c;
-        ti_valid[slot * 2 + 0] = pgm < 0 ? MTa : vm;
-        ti_valid[slot * 2 + 1] = pgn < 0 ? NTa : vn;
-      }
-    }
-    __syncthreads();
-  };
-
-  // long contracted ranges: the k table is a window of KCHUNK steps, refilled
-  // cooperatively (one step per thread) whenever the loader leaves it
-  unsigned ktab_base = 0;
-  auto refill_ktab = [&](unsigned first, unsigned last) {
-    __syncthreads();  // every warp is done reading the previous window
-    ktab_base = first;
-    for (unsigned s = tid; s < (unsigned)KCHUNK && first + s < last; s += THREADS) {
-      long long a, b;
-      int kv;
-      kstep_bases(first + s, a, b, kv);
-      kbA[s] = a;
-      kbB[s] = b;
-      kval[s] = kv;
-    }
-    __syncthreads();
-  };
-
-  auto issue = [&](int st, int slot, unsigned step) {
-    T* dA = sA + st * P::A_ELEMS;
-    T* dB = sB + st * P::B_ELEMS;
-    long long ka, kb;
-    int kvi;
-    ka = kbA[step - ktab_base];
-    kb = kbB[step - ktab_base];
-    kvi = kval[step - ktab_base];
-    stage_kv[st] = kvi;  // every thread writes the same value
-    const unsigned kv = (unsigned)kvi;
-    const T* srcA = A + ti_base[slot * 3 + 0] + ka;
-    const T* srcB = B + ti_base[slot * 3 + 1] + kb;
-    const unsigned m_valid = (unsigned)ti_valid[slot * 2 + 0], n_valid = (unsigned)ti_valid[slot * 2 + 1];
-#pragma unroll
-    for (int i = 0; i < NA; ++i) {
-      const unsigned meta = metaA[i * THREADS + tid];
-      const unsigned r = meta & 0xFFFFu, kk = meta >> 16;
-      if (kk != 0xFFFFu) {
-        const bool ok = (r < m_valid) && (kk < kv);
-        cp_async_zfill<sizeof(T)>(dA + P::idxA(r, kk), ok ? (srcA + gA[i * THREADS + tid]) : A, ok);
-      }
-    }
-#pragma unroll
-    for (int i = 0; i < NB; ++i) {
-      const unsigned meta = metaB[i * THREADS + tid];
-      const unsigned c = meta & 0xFFFFu, kk = meta >> 16;
-      if (kk != 0xFFFFu) {
-        const bool ok = (c < n_valid) && (kk < kv);
-        cp_async_zfill<sizeof(T)>(dB + P::idxB(c, kk), ok ? (srcB + gB[i * THREADS + tid]) : B, ok);
-      }
-    }
-  };
-
-  // loader cursor (runs ahead) and compute cursor over the same stream
-  unsigned l_j = 0, l_step, l_k0, l_k1, g_issue = 0;
-  unsigned c_j = 0, c_step, c_k1, g_comp = 0;
-  work_krange(0, l_k0, l_k1);
-  l_step = l_k0;
-  c_step = l_k0;
-  c_k1 = l_k1;
-
-  auto loader_advance = [&]() {
-    if (l_j < nw) {
-      if (l_step == l_k0) decode_tile(l_j);  // entering a new tile (uniform branch)
-      if (!ktab && (l_step == l_k0 || l_step >= ktab_base + KCHUNK)) refill_ktab(l_step, l_k1);
-      issue((int)(g_issue % STAGES), (int)(l_j % TI), l_step);
-      ++g_issue;
-      ++l_step;
-      if (l_step >= l_k1) {
-        ++l_j;
-        if (l_j < nw) {
-          work_krange(l_j, l_k0, l_k1);
-          l_step = l_k0;
-        }
-      }
-    }
-    cp_async_commit();
-  };
-
-  typename P::Acc acc;
-  P::clear(acc);
-#pragma unroll 1
-  for (int s = 0; s < STAGES - 1; ++s) loader_advance();
-
-  while (c_j < nw) {
-    cp_async_wait<STAGES - 2>();
-    __syncthreads();
-    loader_advance();
-    const int st = (int)(g_comp % STAGES);
-    P::compute(sA + st * P::A_ELEMS, sB + st * P::B_ELEMS, acc, stage_kv[st]);
-    ++g_comp;
-    ++c_step;
-    if (c_step >= c_k1) {
-      // ---- epilogue of tile c_j: store in the parent's index order (strided C)
-      const int slot = (int)(c_j % TI);
-      const long long baseC = ti_base[slot * 3 + 2];
-      const int m_valid = ti_valid[slot * 2 + 0], n_valid = ti_valid[slot * 2 + 1];
-      P::epilogue(
-          acc, scratch,
-          [&](int r, int c, T v) {
-            if (r < m_valid && c < n_valid) {
-              T* p = C + baseC + offMC[r] + offNC[c];
-              if (atomic) {
-                atomic_add_of(p, v);
-              } else if (accumulate) {
-                *p = add_of(*p, v);
-              } else {
-                *p = v;
-              }
-            }
-          },
-          [&](int r, int c, T v0, T v1) {
-            // only called when pair_ok: columns c, c+1 are adjacent and 32B aligned
-            if (r < m_valid && c < n_valid) store_pair_of(C + baseC + offMC[r] + offNC[c], v0, v1);
-          },
-          pair_ok);
-      P::clear(acc);
-      ++c_j;
-      if (c_j < nw) {
-        unsigned k0;
-        work_krange(c_j, k0, c_k1);
-        c_step = k0;
-      }
-    }
-  }
-  cp_async_wait<0>();
-}
-
+#include "gett_ws.cuh"
 
 // ------------------------------------------------------------------ single operand
 // out[o] = sum_s X[off_o(o) + off_s(s)]  (diag via summed strides; contract.py:332-361)

@@ -66,7 +66,7 @@ VARIANT_TILES = {
     VAR_DMMA_64x128: (64, 128, 16),
     VAR_DMMA_256x32: (256, 32, 8),
     VAR_DMMA_256x16: (256, 16, 8),
-    VAR_ROW_128x8: (128, 8, 8),
+    VAR_ROW_128x8: (256, 8, 8),
 }
 
 DTYPE_CODES = {"float32": 0, "float64": 1, "complex64": 2, "complex128": 3}

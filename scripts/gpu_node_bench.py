@@ -19,12 +19,15 @@ from tests.helpers import decode_sliced, load_json, make_arrays
 dtype = sys.argv[1] if len(sys.argv) > 1 else "complex128"
 topk = int(sys.argv[2]) if len(sys.argv) > 2 else 8
 use_ncu = "--ncu" in sys.argv
+rows_only = "--rows" in sys.argv
 rec = next(r for r in load_json("sycamore_m20.json") if r["name"] == "sycamore_m20_appxB")
 spec = cb.TreeSpec(rec["inputs"], rec["output"], rec["size_dict"], rec["path"], decode_sliced(rec["sliced"]))
 plan = cb.ExecPlan(spec.contractions(), spec.inputs, spec.output, spec.size_dict, spec.sliced, dtype=dtype,
                    sm_count=_lib.device_info()["sm_count"])
 es = plan.esize
 nodes = [nd for nd in plan.nodes if nd["kind"] == 0 and not nd["invariant"]]
+if rows_only:
+    nodes = [nd for nd in nodes if nd["sizes"][2] <= 16 or nd["sizes"][1] == 1]
 # rank by ideal cost model: max(flop time at 37 TF, byte time at 6.4 TB/s) is not known a
 # priori, so rank by elements moved + flops/6
 def weight(nd):
