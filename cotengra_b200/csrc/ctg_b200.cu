@@ -118,8 +118,9 @@ int launch_gett_typed(const int64_t* h, const int64_t* d, const void* A, const v
   const int variant = (int)h[W_VARIANT];
   switch (variant) {
     case VAR_SIMT_64x64: return launch_gett_policy<T, SimtPolicy<T, 64, 64, 8, 3>>(h, d, A, B, C, st);
-    case VAR_KRED: return launch_gett_policy<T, KredPolicy<T, 1, 1, 1024, 3>>(h, d, A, B, C, st);
-    case VAR_ROW_128x8: return launch_gett_policy<T, RowPolicy<T, 256, 8, 8, 2>>(h, d, A, B, C, st);
+    case VAR_KRED: return launch_gett_policy<T, KredPolicy<T, 1, 1, 512, 4>>(h, d, A, B, C, st);
+    case VAR_ROW_128x8: return launch_gett_policy<T, RowPolicy<T, 256, 8, 4, 3>>(h, d, A, B, C, st);
+    case VAR_ROW_256x4: return launch_gett_policy<T, RowPolicy<T, 256, 4, 4, 3>>(h, d, A, B, C, st);
     default: break;
   }
   if constexpr (sizeof(T) == 16 || (sizeof(T) == 8 && std::is_same<T, double>::value)) {

@@ -63,7 +63,8 @@ enum : int {
   VAR_DMMA_64x128 = 3,
   VAR_DMMA_256x32 = 4,
   VAR_DMMA_256x16 = 5,
-  VAR_ROW_128x8 = 6    // one output row per thread (HBM-bound skinny nodes)
+  VAR_ROW_128x8 = 6,   // one output row per thread (HBM-bound skinny nodes), N <= 8
+  VAR_ROW_256x4 = 7    // same, N <= 4 (fewer registers -> more resident CTAs)
 };
 
 // ---- single-operand descriptor (cotengra/contract.py:332-361) -------------

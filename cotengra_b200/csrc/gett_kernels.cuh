@@ -171,7 +171,7 @@ struct KredPolicy {
   static constexpr int A_ELEMS = MT * KT, B_ELEMS = NT * KT;
   static constexpr int SCRATCH_ELEMS = MT * NT * (THREADS / 32);
   static constexpr int CONSUMER_REGS = 0, PRODUCER_REGS = 0;
-  static constexpr int MIN_BLOCKS = 1;
+  static constexpr int MIN_BLOCKS = 2;
   struct Acc {
     T v[MT][NT];
   };
@@ -233,7 +233,7 @@ struct RowPolicy {
   static constexpr int A_ELEMS = MT * KT, B_ELEMS = NT * KT;
   static constexpr int SCRATCH_ELEMS = 0;
   static constexpr int CONSUMER_REGS = 0, PRODUCER_REGS = 0;
-  static constexpr int MIN_BLOCKS = 2;
+  static constexpr int MIN_BLOCKS = (NT <= 4 && sizeof(T) * KT * MT <= 16384) ? 3 : 2;
   struct Acc {
     T v[NT];
   };

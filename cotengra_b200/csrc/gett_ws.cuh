@@ -117,6 +117,8 @@ gett_kernel(const int64_t* __restrict__ D, const T* __restrict__ A, const T* __r
   // bit1: every pair of columns (2q, 2q+1) is adjacent in C and 32-byte aligned
   const bool pair_ok = (D[W_FLAGS] & 2) != 0 && !atomic && !accumulate && sizeof(T) == 16;
   const bool ktab = steps_k <= (unsigned)KCHUNK;
+  // no blocked (partial) dim touches the operand: every tabulated element is always valid
+  const bool exactA = pgm < 0 && pgk < 0, exactB = pgn < 0 && pgk < 0;
 
   // k-step bases: a function of the absolute step index only
   auto kstep_bases = [&](unsigned step, long long& a, long long& b, int& kv) {
@@ -164,7 +166,9 @@ gett_kernel(const int64_t* __restrict__ D, const T* __restrict__ A, const T* __r
         }
       }
       gA[i * NPROD + ptid] = g;
-      metaA[i * NPROD + ptid] = r | (kk << 16);
+      // exact tiles (no blocked dim): store the shared-memory index directly
+      metaA[i * NPROD + ptid] = exactA ? (kk == 0xFFFFu ? 0xFFFFFFFFu : (unsigned)P::idxA((int)r, (int)kk))
+                                       : (r | (kk << 16));
     }
     for (int i = 0; i < NB; ++i) {
       unsigned e = ptid + i * NPROD;
@@ -183,7 +187,8 @@ gett_kernel(const int64_t* __restrict__ D, const T* __restrict__ A, const T* __r
         }
       }
       gB[i * NPROD + ptid] = g;
-      metaB[i * NPROD + ptid] = c | (kk << 16);
+      metaB[i * NPROD + ptid] = exactB ? (kk == 0xFFFFu ? 0xFFFFFFFFu : (unsigned)P::idxB((int)c, (int)kk))
+                                       : (c | (kk << 16));
     }
     if (ktab) {
       for (unsigned s = ptid; s < steps_k; s += NPROD) {
@@ -324,22 +329,38 @@ gett_kernel(const int64_t* __restrict__ D, const T* __restrict__ A, const T* __r
         const T* srcA = A + tA + kbA[ti];
         const T* srcB = B + tB + kbB[ti];
         const unsigned kv = (unsigned)kval[ti];
+        if (exactA) {
 #pragma unroll
-        for (int i = 0; i < NA; ++i) {
-          const unsigned meta = metaA[i * NPROD + ptid];
-          const unsigned r = meta & 0xFFFFu, kk = meta >> 16;
-          if (kk != 0xFFFFu) {
-            const bool ok = (r < m_valid) && (kk < kv);
-            cp_async_zfill<sizeof(T)>(dA + P::idxA(r, kk), ok ? (srcA + gA[i * NPROD + ptid]) : A, ok);
+          for (int i = 0; i < NA; ++i) {
+            const unsigned meta = metaA[i * NPROD + ptid];
+            if (meta != 0xFFFFFFFFu) cp_async_zfill<sizeof(T)>(dA + meta, srcA + gA[i * NPROD + ptid], true);
+          }
+        } else {
+#pragma unroll
+          for (int i = 0; i < NA; ++i) {
+            const unsigned meta = metaA[i * NPROD + ptid];
+            const unsigned r = meta & 0xFFFFu, kk = meta >> 16;
+            if (kk != 0xFFFFu) {
+              const bool ok = (r < m_valid) && (kk < kv);
+              cp_async_zfill<sizeof(T)>(dA + P::idxA(r, kk), ok ? (srcA + gA[i * NPROD + ptid]) : A, ok);
+            }
           }
         }
+        if (exactB) {
 #pragma unroll
-        for (int i = 0; i < NB; ++i) {
-          const unsigned meta = metaB[i * NPROD + ptid];
-          const unsigned c = meta & 0xFFFFu, kk = meta >> 16;
-          if (kk != 0xFFFFu) {
-            const bool ok = (c < n_valid) && (kk < kv);
-            cp_async_zfill<sizeof(T)>(dB + P::idxB(c, kk), ok ? (srcB + gB[i * NPROD + ptid]) : B, ok);
+          for (int i = 0; i < NB; ++i) {
+            const unsigned meta = metaB[i * NPROD + ptid];
+            if (meta != 0xFFFFFFFFu) cp_async_zfill<sizeof(T)>(dB + meta, srcB + gB[i * NPROD + ptid], true);
+          }
+        } else {
+#pragma unroll
+          for (int i = 0; i < NB; ++i) {
+            const unsigned meta = metaB[i * NPROD + ptid];
+            const unsigned c = meta & 0xFFFFu, kk = meta >> 16;
+            if (kk != 0xFFFFu) {
+              const bool ok = (c < n_valid) && (kk < kv);
+              cp_async_zfill<sizeof(T)>(dB + P::idxB(c, kk), ok ? (srcB + gB[i * NPROD + ptid]) : B, ok);
+            }
           }
         }
         mbar_arrive_cp_async(&bar_full[st]);

@@ -57,16 +57,17 @@ SDESC_WORDS = OFF_SS + MAX_S * 2
 SDESC_MAGIC = 0x4354474253303031
 
 VAR_SIMT_64x64, VAR_KRED, VAR_DMMA_128x64, VAR_DMMA_64x128, VAR_DMMA_256x32 = 0, 1, 2, 3, 4
-VAR_DMMA_256x16, VAR_ROW_128x8 = 5, 6
+VAR_DMMA_256x16, VAR_ROW_128x8, VAR_ROW_256x4 = 5, 6, 7
 # (MT, NT, KT) of every kernel variant -- must match ctg_b200.cu's dispatch
 VARIANT_TILES = {
     VAR_SIMT_64x64: (64, 64, 8),
-    VAR_KRED: (1, 1, 1024),
+    VAR_KRED: (1, 1, 512),
     VAR_DMMA_128x64: (128, 64, 16),
     VAR_DMMA_64x128: (64, 128, 16),
     VAR_DMMA_256x32: (256, 32, 8),
     VAR_DMMA_256x16: (256, 16, 8),
-    VAR_ROW_128x8: (256, 8, 8),
+    VAR_ROW_128x8: (256, 8, 4),
+    VAR_ROW_256x4: (256, 4, 4),
 }
 
 DTYPE_CODES = {"float32": 0, "float64": 1, "complex64": 2, "complex128": 3}
@@ -317,7 +318,7 @@ def choose_variant(dtype, B, M, N, K, allow_dmma=True):
     if M == 1 and N == 1 and B == 1 and K >= 8192:
         return VAR_KRED
     if N <= 8 and M >= 64:
-        return VAR_ROW_128x8
+        return VAR_ROW_256x4 if N <= 4 else VAR_ROW_128x8
     if allow_dmma and dtype in ("float64", "complex128") and M * N * K >= 1 << 15 and M * N >= 1024:
         if N >= 96:
             return VAR_DMMA_64x128
