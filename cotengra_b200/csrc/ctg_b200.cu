@@ -132,6 +132,16 @@ int launch_gett_typed(const int64_t* h, const int64_t* d, const void* A, const v
       default: break;
     }
   }
+  if constexpr (std::is_same<T, float>::value || std::is_same<T, float2>::value) {
+    // single precision on the tensor pipe: 3xTF32 mma.sync, same tile shapes
+    switch (variant) {
+      case VAR_DMMA_128x64: return launch_gett_policy<T, Tf32Policy<T, 4, 2, 2, 4, 16, 3>>(h, d, A, B, C, st);
+      case VAR_DMMA_64x128: return launch_gett_policy<T, Tf32Policy<T, 2, 4, 2, 4, 16, 3>>(h, d, A, B, C, st);
+      case VAR_DMMA_256x32: return launch_gett_policy<T, Tf32Policy<T, 8, 1, 2, 4, 8, 3>>(h, d, A, B, C, st);
+      case VAR_DMMA_256x16: return launch_gett_policy<T, Tf32Policy<T, 8, 1, 2, 2, 8, 3>>(h, d, A, B, C, st);
+      default: break;
+    }
+  }
   return fail(CTGB_E_VALUE, "unknown kernel variant for this dtype");
 }
 

@@ -391,6 +391,7 @@ struct DmmaPolicy {
   }
 };
 
+#include "tf32_policy.cuh"
 #include "gett_ws.cuh"
 
 // ------------------------------------------------------------------ single operand

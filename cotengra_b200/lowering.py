@@ -319,7 +319,8 @@ def choose_variant(dtype, B, M, N, K, allow_dmma=True):
         return VAR_KRED
     if N <= 8 and M >= 64:
         return VAR_ROW_256x4 if N <= 4 else VAR_ROW_128x8
-    if allow_dmma and dtype in ("float64", "complex128") and M * N * K >= 1 << 15 and M * N >= 1024:
+    # tensor-core tiles: fp64 DMMA for float64/complex128, 3xTF32 for float32/complex64
+    if allow_dmma and M * N * K >= 1 << 15 and M * N >= 1024:
         if N >= 96:
             return VAR_DMMA_64x128
         if N >= 48:
