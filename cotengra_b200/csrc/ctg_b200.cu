@@ -93,6 +93,20 @@ int launch_gett_policy(const int64_t* h, const int64_t* d, const void* A, const 
     CUDA_TRY(cudaFuncSetAttribute(gett_kernel<T, P>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr_dev = dev;
   }
+  if constexpr (P::CONSUMER_REGS > 0) {
+    // setmaxnreg safety: the re-partitioned registers must fit the pool the CTA
+    // was launched with (regs/thread chosen by ptxas x block size), otherwise
+    // setmaxnreg.inc would block forever
+    static thread_local int checked = 0;
+    if (!checked) {
+      cudaFuncAttributes fa;
+      CUDA_TRY(cudaFuncGetAttributes(&fa, gett_kernel<T, P>));
+      const long pool = (long)fa.numRegs * (P::THREADS + PRODUCER_THREADS);
+      const long want = (long)P::CONSUMER_REGS * P::THREADS + (long)P::PRODUCER_REGS * PRODUCER_THREADS;
+      if (want > pool) return fail(CTGB_E_CUDA, "setmaxnreg budget exceeds the launch register pool");
+      checked = 1;
+    }
+  }
   static thread_local int occ = 0;
   if (occ == 0) {
     CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, gett_kernel<T, P>, P::THREADS + PRODUCER_THREADS, smem));
@@ -118,7 +132,7 @@ int launch_gett_typed(const int64_t* h, const int64_t* d, const void* A, const v
   const int variant = (int)h[W_VARIANT];
   switch (variant) {
     case VAR_SIMT_64x64: return launch_gett_policy<T, SimtPolicy<T, 64, 64, 8, 3>>(h, d, A, B, C, st);
-    case VAR_KRED: return launch_gett_policy<T, KredPolicy<T, 1, 1, 512, 4>>(h, d, A, B, C, st);
+    case VAR_KRED: return launch_gett_policy<T, KredPolicy<T, 1, 1, 512, 6>>(h, d, A, B, C, st);
     case VAR_ROW_128x8: return launch_gett_policy<T, RowPolicy<T, 256, 8, 4, 3>>(h, d, A, B, C, st);
     case VAR_ROW_256x4: return launch_gett_policy<T, RowPolicy<T, 256, 4, 4, 3>>(h, d, A, B, C, st);
     default: break;

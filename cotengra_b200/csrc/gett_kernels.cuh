@@ -98,16 +98,16 @@ __device__ __forceinline__ void cp_async_wait() {
   asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory");
 }
 
+// sum of NON-NEGATIVE 64-bit offsets over the warp with three redux.sync
+// (24-bit chunks cannot overflow 32 bits when added over 32 lanes)
 __device__ __forceinline__ long long warp_sum_ll(long long v) {
-#pragma unroll
-  for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(0xffffffffu, v, d);
-  return v;
+  const unsigned long long u = (unsigned long long)v;
+  const unsigned lo = __reduce_add_sync(0xffffffffu, (unsigned)(u & 0xFFFFFFull));
+  const unsigned mid = __reduce_add_sync(0xffffffffu, (unsigned)((u >> 24) & 0xFFFFFFull));
+  const unsigned hi = __reduce_add_sync(0xffffffffu, (unsigned)(u >> 48));
+  return (long long)((unsigned long long)lo + ((unsigned long long)mid << 24) + ((unsigned long long)hi << 48));
 }
-__device__ __forceinline__ int warp_sum_i(int v) {
-#pragma unroll
-  for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(0xffffffffu, v, d);
-  return v;
-}
+__device__ __forceinline__ int warp_sum_i(int v) { return (int)__reduce_add_sync(0xffffffffu, (unsigned)v); }
 
 // ------------------------------------------------------------------ policies
 // A policy fixes the CTA tile (MT x NT x KT), the pipeline depth, the shared
@@ -122,6 +122,7 @@ struct SimtPolicy {
   static constexpr int A_ELEMS = MT * KT, B_ELEMS = NT * KT;
   static constexpr int SCRATCH_ELEMS = 0;
   static constexpr int CONSUMER_REGS = 0, PRODUCER_REGS = 0;
+  static constexpr bool HAS_BCACHE = false;
   static constexpr int MIN_BLOCKS = sizeof(T) == 16 ? 1 : 2;
   struct Acc {
     T v[TM][TN];
@@ -171,6 +172,7 @@ struct KredPolicy {
   static constexpr int A_ELEMS = MT * KT, B_ELEMS = NT * KT;
   static constexpr int SCRATCH_ELEMS = MT * NT * (THREADS / 32);
   static constexpr int CONSUMER_REGS = 0, PRODUCER_REGS = 0;
+  static constexpr bool HAS_BCACHE = false;
   static constexpr int MIN_BLOCKS = 2;
   struct Acc {
     T v[MT][NT];
@@ -223,54 +225,89 @@ struct KredPolicy {
   }
 };
 
-// Skinny nodes (few kept indices on the small operand: N <= 8) are HBM-bound:
-// one output row per thread, the small operand broadcast from shared memory,
-// small footprint so that many CTAs per SM keep enough loads in flight.
+// Skinny nodes (few kept indices on the small operand: N <= 8) are HBM-bound.
+// 128 consumer threads, two output rows per thread; the small operand is
+// broadcast from shared memory, or -- when its tile is the same for every work
+// item (all of K and N inside the tile, no batch) -- read ONCE into registers
+// (broadcast LDS.128 of B were 60% of the shared-memory wavefronts under ncu).
 template <typename T, int MT_, int NT_, int KT_, int STAGES_>
 struct RowPolicy {
   static constexpr int MT = MT_, NT = NT_, KT = KT_, STAGES = STAGES_;
-  static constexpr int THREADS = MT;
+  static constexpr int THREADS = MT / 2;
   static constexpr int A_ELEMS = MT * KT, B_ELEMS = NT * KT;
   static constexpr int SCRATCH_ELEMS = 0;
+  // (no setmaxnreg here: the CTA's register pool is regs-per-thread as chosen by
+  // ptxas times the block size, and an .inc beyond that pool would block forever)
   static constexpr int CONSUMER_REGS = 0, PRODUCER_REGS = 0;
-  static constexpr int MIN_BLOCKS = (NT <= 4 && sizeof(T) * KT * MT <= 16384) ? 3 : 2;
+  static constexpr int MIN_BLOCKS = 2;
+  static constexpr bool HAS_BCACHE = sizeof(T) * KT * NT <= 256;
+  struct BCache {
+    T v[KT][NT];
+  };
   struct Acc {
-    T v[NT];
+    T v[2][NT];
   };
   __device__ static __forceinline__ int idxA(int r, int kk) { return kk * MT + r; }
   __device__ static __forceinline__ int idxB(int c, int kk) { return kk * NT + c; }
   __device__ static __forceinline__ void clear(Acc& acc) {
 #pragma unroll
-    for (int j = 0; j < NT; ++j) acc.v[j] = zero_of<T>();
+    for (int j = 0; j < NT; ++j) acc.v[0][j] = acc.v[1][j] = zero_of<T>();
+  }
+  __device__ static __forceinline__ void load_b(const T* __restrict__ sB, BCache& bc) {
+#pragma unroll
+    for (int kk = 0; kk < KT; ++kk)
+#pragma unroll
+      for (int j = 0; j < NT; ++j) bc.v[kk][j] = sB[kk * NT + j];
+  }
+  __device__ static __forceinline__ void compute_cached(const T* __restrict__ sA, const BCache& bc, Acc& acc,
+                                                        int kvalid, int ncols) {
+#pragma unroll
+    for (int kk = 0; kk < KT; ++kk) {
+      if (kk < kvalid) {
+        const T a0 = sA[kk * MT + threadIdx.x], a1 = sA[kk * MT + threadIdx.x + THREADS];
+#pragma unroll
+        for (int j = 0; j < NT; ++j)
+          if (j < ncols) {
+            mac(acc.v[0][j], a0, bc.v[kk][j]);
+            mac(acc.v[1][j], a1, bc.v[kk][j]);
+          }
+      }
+    }
   }
   __device__ static __forceinline__ void compute(const T* __restrict__ sA, const T* __restrict__ sB, Acc& acc,
                                                  int kvalid, int ncols) {
 #pragma unroll 1
     for (int kk = 0; kk < KT; ++kk) {
       if (kk >= kvalid) break;
-      const T a = sA[kk * MT + threadIdx.x];
+      const T a0 = sA[kk * MT + threadIdx.x], a1 = sA[kk * MT + threadIdx.x + THREADS];
 #pragma unroll
       for (int j = 0; j < NT; ++j) {
         if (j >= ncols) break;
-        mac(acc.v[j], a, sB[kk * NT + j]);
+        const T b = sB[kk * NT + j];
+        mac(acc.v[0][j], a0, b);
+        mac(acc.v[1][j], a1, b);
       }
     }
   }
   template <typename F, typename F2>
   __device__ static __forceinline__ void epilogue(Acc& acc, T* scratch, F&& store, F2&& store_pair, bool pair_ok,
                                                   int ncols) {
-    if (pair_ok) {
-      // the row's columns are adjacent in C: 32-byte (256-bit) stores, full sectors
 #pragma unroll
-      for (int j = 0; j < NT; j += 2) {
-        if (j >= ncols) break;
-        store_pair((int)threadIdx.x, j, acc.v[j], acc.v[j + 1]);
-      }
-    } else {
+    for (int h = 0; h < 2; ++h) {
+      const int r = (int)threadIdx.x + h * THREADS;
+      if (pair_ok) {
+        // the row's columns are adjacent in C: 32-byte (256-bit) stores, full sectors
 #pragma unroll
-      for (int j = 0; j < NT; ++j) {
-        if (j >= ncols) break;
-        store((int)threadIdx.x, j, acc.v[j]);
+        for (int j = 0; j < NT; j += 2) {
+          if (j >= ncols) break;
+          store_pair(r, j, acc.v[h][j], acc.v[h][j + 1]);
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < NT; ++j) {
+          if (j >= ncols) break;
+          store(r, j, acc.v[h][j]);
+        }
       }
     }
   }
@@ -297,6 +334,7 @@ struct DmmaPolicy {
   static constexpr int SCRATCH_ELEMS = 0;
   // 8 consumer warps x 232 + 4 producer warps x 40 registers = 64512 <= 65536
   static constexpr int CONSUMER_REGS = (THREADS == 256) ? 232 : 0, PRODUCER_REGS = 40;
+  static constexpr bool HAS_BCACHE = false;
   static constexpr int MIN_BLOCKS = 1;
   static_assert(KT % 4 == 0, "KT must be a multiple of the DMMA k");
   struct Acc {

@@ -57,11 +57,25 @@ __device__ __forceinline__ void reg_dealloc() {
   asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;\n" ::"n"(REGS));
 }
 
+template <class P, bool HAS>
+struct BCacheOf {
+  struct type {};
+};
+template <class P>
+struct BCacheOf<P, true> {
+  using type = typename P::BCache;
+};
+
 template <class P>
 struct GettSmem {
   static constexpr int NA = (P::A_ELEMS + PRODUCER_THREADS - 1) / PRODUCER_THREADS;
   static constexpr int NB = (P::B_ELEMS + PRODUCER_THREADS - 1) / PRODUCER_THREADS;
-  static constexpr int TI = P::STAGES + 1;  // tile-info ring
+  // tile-info ring.  STAGES + 2 slots: the producer decodes tile j+TI right after
+  // issuing tile j+TI-1, whose first stage needed the "empty" arrival of every
+  // consumer warp for tile j+1 -- i.e. all of them are past the epilogue of tile
+  // j, the last reader of slot j % TI.  (STAGES + 1 is one too few: the decode
+  // runs BEFORE the producer waits on the stage it will fill.)
+  static constexpr int TI = P::STAGES + 2;
   template <typename T>
   static constexpr size_t bytes() {
     return sizeof(T) * ((size_t)P::STAGES * (P::A_ELEMS + P::B_ELEMS) + P::SCRATCH_ELEMS)  // ring + scratch
@@ -117,6 +131,11 @@ gett_kernel(const int64_t* __restrict__ D, const T* __restrict__ A, const T* __r
   // bit1: every pair of columns (2q, 2q+1) is adjacent in C and 32-byte aligned
   const bool pair_ok = (D[W_FLAGS] & 2) != 0 && !atomic && !accumulate && sizeof(T) == 16;
   const bool ktab = steps_k <= (unsigned)KCHUNK;
+  // bit2: every tile-grid extent is a power of two -> digits by shift/mask, no idiv
+  const bool g_pow2 = (D[W_FLAGS] & 4) != 0;
+  auto digit_of = [&](unsigned idx, unsigned div, unsigned ext) -> unsigned {
+    return g_pow2 ? ((idx >> (31 - __clz(div))) & (ext - 1)) : ((idx / div) % ext);
+  };
   // no blocked (partial) dim touches the operand: every tabulated element is always valid
   const bool exactA = pgm < 0 && pgk < 0, exactB = pgn < 0 && pgk < 0;
 
@@ -256,16 +275,25 @@ gett_kernel(const int64_t* __restrict__ D, const T* __restrict__ A, const T* __r
       // per grid dim; n fastest so neighbouring CTAs share A tiles in L2)
       const int slot = (int)(j % TI);
       if (ptid < 32) {
-        unsigned t = (blockIdx.x + j * gridDim.x) % tiles_all;
-        const unsigned in_ = t % tiles_n;
-        t /= tiles_n;
-        const unsigned im_ = t % tiles_m;
-        const unsigned ib_ = t / tiles_m;
+        unsigned t = blockIdx.x + j * gridDim.x;
+        if (splitk > 1) t %= tiles_all;
+        unsigned in_, im_, ib_;
+        if (g_pow2) {
+          in_ = t & (tiles_n - 1);
+          t >>= 31 - __clz(tiles_n);
+          im_ = t & (tiles_m - 1);
+          ib_ = t >> (31 - __clz(tiles_m));
+        } else {
+          in_ = t % tiles_n;
+          t /= tiles_n;
+          im_ = t % tiles_m;
+          ib_ = t / tiles_m;
+        }
         long long a = 0, b = 0, c = 0;
         int vm = 0, vn = 0;
         for (int q = lane; q < n_gm; q += 32) {
           const int64_t* G = D + OFF_GM + q * 4;
-          unsigned dig = (im_ / (unsigned)G[1]) % (unsigned)G[0];
+          unsigned dig = digit_of(im_, (unsigned)G[1], (unsigned)G[0]);
           a += (long long)dig * G[2];
           c += (long long)dig * G[3];
           if (q == pgm)
@@ -274,7 +302,7 @@ gett_kernel(const int64_t* __restrict__ D, const T* __restrict__ A, const T* __r
         }
         for (int q = lane; q < n_gn; q += 32) {
           const int64_t* G = D + OFF_GN + q * 4;
-          unsigned dig = (in_ / (unsigned)G[1]) % (unsigned)G[0];
+          unsigned dig = digit_of(in_, (unsigned)G[1], (unsigned)G[0]);
           b += (long long)dig * G[2];
           c += (long long)dig * G[3];
           if (q == pgn)
@@ -283,7 +311,7 @@ gett_kernel(const int64_t* __restrict__ D, const T* __restrict__ A, const T* __r
         }
         for (int q = lane; q < n_gb; q += 32) {
           const int64_t* G = D + OFF_GB + q * 5;
-          unsigned dig = (ib_ / (unsigned)G[1]) % (unsigned)G[0];
+          unsigned dig = digit_of(ib_, (unsigned)G[1], (unsigned)G[0]);
           a += (long long)dig * G[2];
           b += (long long)dig * G[3];
           c += (long long)dig * G[4];
@@ -378,6 +406,10 @@ gett_kernel(const int64_t* __restrict__ D, const T* __restrict__ A, const T* __r
     typename P::Acc acc;
     P::clear(acc);
     unsigned g = 0;
+    // the small operand's tile is identical for every work item of this launch
+    [[maybe_unused]] const bool b_invariant = steps_k == 1 && n_gn == 0 && n_gb == 0;
+    [[maybe_unused]] bool b_loaded = false;
+    [[maybe_unused]] typename BCacheOf<P, P::HAS_BCACHE>::type bcache;
     for (unsigned j = 0; j < nw; ++j) {
       unsigned k0, k1;
       work_krange(j, k0, k1);
@@ -389,7 +421,18 @@ gett_kernel(const int64_t* __restrict__ D, const T* __restrict__ A, const T* __r
           kv = min(ktext, kfull - dig * ktext) * kw;
         }
         mbar_wait(&bar_full[st], (g / STAGES) & 1);
-        P::compute(sA + st * P::A_ELEMS, sB + st * P::B_ELEMS, acc, kv, NTa);
+        if constexpr (P::HAS_BCACHE) {
+          if (b_invariant) {
+            if (!b_loaded) {
+              P::load_b(sB + st * P::B_ELEMS, bcache);
+              b_loaded = true;
+            }
+            P::compute_cached(sA + st * P::A_ELEMS, bcache, acc, kv, NTa);
+          } else {
+            P::compute(sA + st * P::A_ELEMS, sB + st * P::B_ELEMS, acc, kv, NTa);
+          }
+        } else
+          P::compute(sA + st * P::A_ELEMS, sB + st * P::B_ELEMS, acc, kv, NTa);
         __syncwarp();
         if (lane == 0) mbar_arrive(&bar_empty[st]);
       }

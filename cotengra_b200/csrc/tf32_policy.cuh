@@ -43,6 +43,7 @@ struct Tf32Policy {
   static constexpr int A_ELEMS = MT * KT, B_ELEMS = NT * KT;
   static constexpr int SCRATCH_ELEMS = 0;
   static constexpr int CONSUMER_REGS = (THREADS == 256) ? 232 : 0, PRODUCER_REGS = 40;
+  static constexpr bool HAS_BCACHE = false;
   static constexpr int MIN_BLOCKS = 1;
   static_assert(KT % 8 == 0, "KT must be a multiple of the MMA k");
   struct Acc {

@@ -238,7 +238,7 @@ class ExecPlan:
             dst = _T(dims.out_shape, row_major_strides(dims.out_shape), 1, A.variant or Bt.variant)
             a, b = (Bt, A) if plan.swapped else (A, Bt)
             nodes.append(dict(kind=0, a=a, b=b, c=dst, words=plan.words, root=is_root, plan=plan,
-                              sizes=plan.sizes))
+                              sizes=plan.sizes, dims=dims, acc=acc, dense=dense))
             tensors.append(dst)
             cur[p] = dst
 

@@ -434,7 +434,11 @@ def build_pair_desc(dims: PairDims, dtype, accumulate=False, sm_count=148,
         and all(g[3] % 2 == 0 for g in gm) and all(g[3] % 2 == 0 for g in gn)
         and all(g[4] % 2 == 0 for g in gb)
     )
-    W[W_FLAGS] = (1 if accumulate else 0) | (2 if pair_ok else 0)
+    # bit2: all tile-grid extents are powers of two (Sycamore: always) -> the
+    # producers decode tile indices with shifts/masks instead of idiv
+    is_p2 = lambda e: e > 0 and (e & (e - 1)) == 0  # noqa: E731
+    grid_pow2 = all(is_p2(g[0]) for g in gm + gn + gb)
+    W[W_FLAGS] = (1 if accumulate else 0) | (2 if pair_ok else 0) | (4 if grid_pow2 else 0)
     W[W_VARIANT] = variant
     W[W_CELEMS] = int(c_dense_elems)
 
