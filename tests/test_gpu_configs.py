@@ -1,0 +1,101 @@
+"""GPU parity on the BASELINE.json configurations other than the bench line:
+config 2 (8x8 PEPS, bond 6, complex64, unsliced), config 3 (Sycamore m10
+amplitude, real gate tensors, unsliced) and config 4 (Sycamore m12, 256 slices)."""
+
+import json
+import os
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+import cotengra_b200 as cb  # noqa: E402
+from oracle import ctg_oracle as orc  # noqa: E402
+from tests.helpers import GOLDEN_DIR, decode_sliced, load_json, load_npz, make_arrays, rel_err  # noqa: E402
+
+
+def _circuit(name):
+    path = os.path.join(GOLDEN_DIR, "circuits.json")
+    if not os.path.exists(path):
+        pytest.skip("circuits.json not generated")
+    recs = json.load(open(path))
+    if name not in recs:
+        pytest.skip(f"{name} fixture not generated")
+    rec = recs[name]
+    flat = load_npz("circuits_arrays.npz")[f"{name}_arrays_flat"]
+    spec = cb.TreeSpec.from_dict(rec["spec"])
+    arrays, off = [], 0
+    for shape in spec.shapes():
+        n = int(np.prod(shape))
+        arrays.append(flat[off:off + n].reshape(shape))
+        off += n
+    assert off == flat.size
+    return rec, spec, arrays
+
+
+def test_config2_peps8x8_bond6():
+    rec = next(r for r in load_json("trees.json") if r["name"] == "peps8x8_d2")
+    size_dict = {ix: 6 for ix in rec["size_dict"]}
+    spec = cb.TreeSpec(rec["inputs"], rec["output"], size_dict, rec["path"])
+    arrays = make_arrays(spec.shapes(), "complex128", seed=11, scale=0.35)
+    want = orc.run_contractions(spec.contractions(), arrays)  # numpy oracle, complex128
+    got = cb.contract_tree(spec, arrays)
+    assert rel_err(got, want) < 1e-10
+    got64 = cb.contract_tree(spec, [a.astype(np.complex64) for a in arrays])
+    assert got64.dtype == np.complex64
+    # the reference's own c64 and c128 runs differ by 8e-6 on this network
+    assert rel_err(got64, want) < 5e-5
+
+
+def test_config3_sycamore_m10_amplitude():
+    rec, spec, arrays = _circuit("m10")
+    vals = load_npz("circuits_values.npz")
+    want = vals["m10_amplitude"]  # reference numpy path, real gate tensors
+    got = cb.contract_tree(spec, arrays)
+    assert rel_err(got, want) < 1e-10
+    got64 = cb.contract_tree(spec, [a.astype(np.complex64) for a in arrays])
+    assert rel_err(got64, want) < 1e-4
+    # slices of the further-sliced copy against the reference
+    small = cb.TreeSpec.from_dict(rec["small_spec"])
+    ex = cb.TreeExecutor(small, dtype="complex128")
+    import torch
+
+    dev = [torch.from_numpy(np.ascontiguousarray(a)).cuda() for a in arrays]
+    for i in (0, 3):
+        g = ex.contract_device(dev, begin=i, step=1, count=1).cpu().numpy()
+        assert rel_err(g, vals[f"m10_small_slice{i}"]) < 1e-10
+
+
+def test_config4_sycamore_m12_sliced():
+    rec, spec, arrays = _circuit("m12")
+    vals = load_npz("circuits_values.npz")
+    import torch
+
+    dev = [torch.from_numpy(np.ascontiguousarray(a)).cuda() for a in arrays]
+    small = cb.TreeSpec.from_dict(rec["small_spec"])
+    ex = cb.TreeExecutor(small, dtype="complex128")
+    for i in (0, 3):
+        g = ex.contract_device(dev, begin=i, step=1, count=1).cpu().numpy()
+        assert rel_err(g, vals[f"m12_small_slice{i}"]) < 1e-10
+    # the 256-slice tree itself (W = 2^32 per slice at complex64 = 32 GiB tensors,
+    # > 2^31 elements: 64-bit offsets): one slice must equal the sum of the slices
+    # of the further-sliced tree that refine it
+    if not os.environ.get("CTGB_RUN_HUGE"):
+        return
+    ex_big = cb.TreeExecutor(spec, dtype="complex64")
+    dev64 = [t.to(torch.complex64) for t in dev]
+    big = ex_big.contract_device(dev64, begin=0, step=1, count=1).cpu().numpy()
+    key0 = spec.slice_key(0)
+    extra = [s for s in small.sliced if s[0] not in key0]
+    assert len(extra) <= 12
+    from itertools import product
+
+    from tests.slicing_util import slice_id
+
+    tot = 0
+    for digs in product(*[range(s[1]) for s in extra]):
+        key = dict(key0)
+        key.update({s[0]: d for s, d in zip(extra, digs)})
+        tot = tot + ex.contract_device(dev, begin=slice_id(small, key), step=1, count=1).cpu().numpy()
+    assert rel_err(big, tot) < 1e-4
