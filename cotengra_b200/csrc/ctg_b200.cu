@@ -128,8 +128,37 @@ int launch_gett_policy(const int64_t* h, const int64_t* d, const void* A, const 
 }
 
 template <typename T>
+int launch_rowstream(const int64_t* h, const int64_t* d, const void* A, const void* B, void* C, cudaStream_t st) {
+  DevInfo& di = devinfo();
+  if (!di.ok) return fail(CTGB_E_CUDA, "no CUDA device");
+  const int N = (int)h[W_NTA], K = (int)h[W_KTA];
+  if (N > 8 || K > 8 || h[W_TILES_N] != 1 || h[W_TILES_B] != 1 || h[W_STEPS_K] != 1 || h[W_SPLITK] != 1 ||
+      h[W_PGM] >= 0 && (h[W_MFULL] % h[W_MTEXT]) != 0 || h[W_PGN] >= 0 || h[W_PGK] >= 0)
+    return fail(CTGB_E_VALUE, "descriptor does not fit the row-stream kernel");
+  const unsigned long long M = (unsigned long long)h[W_MTA] * (unsigned long long)h[W_TILES_M];
+  if (M >= (1ull << 32)) return fail(CTGB_E_VALUE, "too many rows for the row-stream kernel");
+  unsigned long long blocks = (M + 255) / 256;
+  const unsigned long long cap = (unsigned long long)di.sms * 8;
+  if (blocks > cap) blocks = cap;
+  if (blocks == 0) return CTGB_OK;
+  const T* a = (const T*)A;
+  const T* b = (const T*)B;
+  T* c = (T*)C;
+  if (N <= 4 && K <= 4)
+    rowstream_kernel<T, 4, 4, true><<<(unsigned)blocks, 256, 0, st>>>(d, a, b, c);
+  else if (N <= 2)
+    rowstream_kernel<T, 2, 8, true><<<(unsigned)blocks, 256, 0, st>>>(d, a, b, c);
+  else
+    rowstream_kernel<T, 8, 8, false><<<(unsigned)blocks, 256, 0, st>>>(d, a, b, c);
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  CUDA_TRY(cudaGetLastError());
+  return CTGB_OK;
+}
+
+template <typename T>
 int launch_gett_typed(const int64_t* h, const int64_t* d, const void* A, const void* B, void* C, cudaStream_t st) {
   const int variant = (int)h[W_VARIANT];
+  if (variant == VAR_ROWSTREAM) return launch_rowstream<T>(h, d, A, B, C, st);
   switch (variant) {
     case VAR_SIMT_64x64: return launch_gett_policy<T, SimtPolicy<T, 64, 64, 8, 3>>(h, d, A, B, C, st);
     case VAR_KRED: return launch_gett_policy<T, KredPolicy<T, 1, 1, 512, 6>>(h, d, A, B, C, st);

@@ -36,7 +36,8 @@ enum : int {
   W_PGN = 21, W_NFULL = 22, W_NTEXT = 23, W_NW = 24,
   W_PGK = 25, W_KFULL = 26, W_KTEXT = 27, W_KW = 28,
   W_NLDA = 29, W_NLDB = 30,
-  W_FLAGS = 31,        // bit0: accumulate into C (beta = 1)
+  W_FLAGS = 31,        // bit0: accumulate into C; bit1: column pairs adjacent+aligned in C;
+                       // bit2: tile-grid extents are powers of two; bit3: all m dims are powers of two
   W_VARIANT = 32,      // kernel variant chosen by the host
   W_CELEMS = 33,       // elements of a dense C (memset before split-K atomics); 0: strided C
   W_HDR = 40,
@@ -64,7 +65,8 @@ enum : int {
   VAR_DMMA_256x32 = 4,
   VAR_DMMA_256x16 = 5,
   VAR_ROW_128x8 = 6,   // one output row per thread (HBM-bound skinny nodes), N <= 8
-  VAR_ROW_256x4 = 7    // same, N <= 4 (fewer registers -> more resident CTAs)
+  VAR_ROW_256x4 = 7,   // same, N <= 4 (fewer registers -> more resident CTAs)
+  VAR_ROWSTREAM = 8    // N, K <= 8, exact tiles, no batch: thread-per-row straight from global memory
 };
 
 // ---- single-operand descriptor (cotengra/contract.py:332-361) -------------

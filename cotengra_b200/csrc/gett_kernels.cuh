@@ -430,6 +430,7 @@ struct DmmaPolicy {
 };
 
 #include "tf32_policy.cuh"
+#include "rowstream.cuh"
 #include "gett_ws.cuh"
 
 // ------------------------------------------------------------------ single operand

@@ -1,0 +1,147 @@
+// rowstream.cuh -- streaming kernel for skinny nodes (N <= 8, K <= 8, no batch):
+// one output row per thread, operands read straight from global memory
+// (coalesced 128-bit loads when consecutive rows are adjacent in A, which the
+// host's dim ordering arranges), the small operand held in registers or
+// broadcast from shared memory, 256-bit stores.  No shared-memory staging and
+// no producer warps: HBM-bound nodes want LSU wavefronts and instructions per
+// row at the minimum and many resident warps to cover latency (ncu showed the
+// staged row policy at 61-69 % LSU data-pipe utilisation, 4.4 TB/s).
+// (included inside namespace ctgb)
+#pragma once
+
+constexpr int RS_MAXDIMS = MAX_T + MAX_G;
+
+template <typename T, int NMAX, int KMAX, bool BREG>
+__global__ void __launch_bounds__(256)
+rowstream_kernel(const int64_t* __restrict__ D, const T* __restrict__ A, const T* __restrict__ B, T* __restrict__ C) {
+  __shared__ long long s_akoff[KMAX], s_bkoff[KMAX], s_bnoff[NMAX], s_cnoff[NMAX];
+  __shared__ long long s_msA[RS_MAXDIMS], s_msC[RS_MAXDIMS];
+  __shared__ unsigned s_mext[RS_MAXDIMS];
+  __shared__ T s_B[KMAX * NMAX];
+  const int tid = threadIdx.x;
+  const int n_tm = (int)D[W_NTM], n_gm = (int)D[W_NGM], n_tk = (int)D[W_NTK], n_tn = (int)D[W_NTN];
+  const int K = (int)D[W_KTA], N = (int)D[W_NTA];
+  const int n_m = n_tm + n_gm;
+  const bool accumulate = (D[W_FLAGS] & 1) != 0;
+  const bool pair_ok = (D[W_FLAGS] & 2) != 0 && !accumulate && sizeof(T) == 16;
+  const bool pow2 = (D[W_FLAGS] & 8) != 0;  // every m dim (tile and grid) is a power of two
+  // m dims in enumeration order: tile dims (dim 0 fastest) then grid dims
+  for (int d = tid; d < n_m; d += blockDim.x) {
+    if (d < n_tm) {
+      const int64_t* L = D + OFF_TM + d * 3;
+      s_mext[d] = (unsigned)L[0];
+      s_msA[d] = L[1];
+      s_msC[d] = L[2];
+    } else {
+      const int64_t* G = D + OFF_GM + (d - n_tm) * 4;
+      s_mext[d] = (unsigned)G[0];
+      s_msA[d] = G[2];
+      s_msC[d] = G[3];
+    }
+  }
+  if (tid < KMAX) {
+    long long a = 0, b = 0;
+    if (tid < K) {
+      unsigned e = tid;
+      for (int d = 0; d < n_tk; ++d) {
+        const int64_t* L = D + OFF_TK + d * 3;
+        unsigned ext = (unsigned)L[0];
+        a += (long long)(e % ext) * L[1];
+        b += (long long)(e % ext) * L[2];
+        e /= ext;
+      }
+    }
+    s_akoff[tid] = a;
+    s_bkoff[tid] = b;
+  }
+  if (tid >= 32 && tid < 32 + NMAX) {
+    const int c = tid - 32;
+    long long b = 0, o = 0;
+    if (c < N) {
+      unsigned e = c;
+      for (int d = 0; d < n_tn; ++d) {
+        const int64_t* L = D + OFF_TN + d * 3;
+        unsigned ext = (unsigned)L[0];
+        b += (long long)(e % ext) * L[1];
+        o += (long long)(e % ext) * L[2];
+        e /= ext;
+      }
+    }
+    s_bnoff[c] = b;
+    s_cnoff[c] = o;
+  }
+  __syncthreads();
+  if (tid < KMAX * NMAX) {
+    const int kk = tid / NMAX, c = tid % NMAX;
+    s_B[tid] = (kk < K && c < N) ? B[s_bkoff[kk] + s_bnoff[c]] : zero_of<T>();
+  }
+  __syncthreads();
+  [[maybe_unused]] T breg[BREG ? KMAX : 1][BREG ? NMAX : 1];
+  if constexpr (BREG) {
+#pragma unroll
+    for (int kk = 0; kk < KMAX; ++kk)
+#pragma unroll
+      for (int c = 0; c < NMAX; ++c) breg[kk][c] = s_B[kk * NMAX + c];
+  }
+  long long akoff[KMAX];
+#pragma unroll
+  for (int kk = 0; kk < KMAX; ++kk) akoff[kk] = s_akoff[kk];
+
+  const unsigned long long M = (unsigned long long)D[W_MTA] * (unsigned long long)D[W_TILES_M];
+  const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
+  for (unsigned long long m = (unsigned long long)blockIdx.x * blockDim.x + tid; m < M; m += stride) {
+    unsigned e = (unsigned)m;
+    long long oa = 0, oc = 0;
+    if (pow2) {
+      for (int d = 0; d < n_m; ++d) {
+        const unsigned ext = s_mext[d];
+        const unsigned dig = e & (ext - 1);
+        e >>= 31 - __clz(ext);
+        oa += (long long)dig * s_msA[d];
+        oc += (long long)dig * s_msC[d];
+      }
+    } else {
+      for (int d = 0; d < n_m; ++d) {
+        const unsigned ext = s_mext[d];
+        const unsigned dig = e % ext;
+        e /= ext;
+        oa += (long long)dig * s_msA[d];
+        oc += (long long)dig * s_msC[d];
+      }
+    }
+    T acc[NMAX];
+#pragma unroll
+    for (int c = 0; c < NMAX; ++c) acc[c] = zero_of<T>();
+    const T* pa = A + oa;
+    T a[KMAX];
+#pragma unroll
+    for (int kk = 0; kk < KMAX; ++kk)
+      if (kk < K) a[kk] = pa[akoff[kk]];
+#pragma unroll
+    for (int kk = 0; kk < KMAX; ++kk) {
+      if (kk < K) {
+#pragma unroll
+        for (int c = 0; c < NMAX; ++c) {
+          if constexpr (BREG) {
+            mac(acc[c], a[kk], breg[kk][c]);
+          } else {
+            if (c < N) mac(acc[c], a[kk], s_B[kk * NMAX + c]);
+          }
+        }
+      }
+    }
+    T* pc = C + oc;
+    if (pair_ok) {
+#pragma unroll
+      for (int c = 0; c < NMAX; c += 2)
+        if (c < N) store_pair_of(pc + s_cnoff[c], acc[c], acc[c + 1]);
+    } else {
+#pragma unroll
+      for (int c = 0; c < NMAX; ++c)
+        if (c < N) {
+          T* p = pc + s_cnoff[c];
+          *p = accumulate ? add_of(*p, acc[c]) : acc[c];
+        }
+    }
+  }
+}

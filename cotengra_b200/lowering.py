@@ -57,7 +57,7 @@ SDESC_WORDS = OFF_SS + MAX_S * 2
 SDESC_MAGIC = 0x4354474253303031
 
 VAR_SIMT_64x64, VAR_KRED, VAR_DMMA_128x64, VAR_DMMA_64x128, VAR_DMMA_256x32 = 0, 1, 2, 3, 4
-VAR_DMMA_256x16, VAR_ROW_128x8, VAR_ROW_256x4 = 5, 6, 7
+VAR_DMMA_256x16, VAR_ROW_128x8, VAR_ROW_256x4, VAR_ROWSTREAM = 5, 6, 7, 8
 # (MT, NT, KT) of every kernel variant -- must match ctg_b200.cu's dispatch
 VARIANT_TILES = {
     VAR_SIMT_64x64: (64, 64, 8),
@@ -68,6 +68,7 @@ VARIANT_TILES = {
     VAR_DMMA_256x16: (256, 16, 8),
     VAR_ROW_128x8: (256, 8, 4),
     VAR_ROW_256x4: (256, 4, 4),
+    VAR_ROWSTREAM: (256, 8, 8),
 }
 
 DTYPE_CODES = {"float32": 0, "float64": 1, "complex64": 2, "complex128": 3}
@@ -314,9 +315,11 @@ class PairPlan:
     splitk: int
 
 
-def choose_variant(dtype, B, M, N, K, allow_dmma=True):
+def choose_variant(dtype, B, M, N, K, allow_dmma=True, allow_stream=True):
     if M == 1 and N == 1 and B == 1 and K >= 8192:
         return VAR_KRED
+    if N <= 8 and K <= 8 and B == 1 and 64 <= M < 1 << 32 and allow_stream:
+        return VAR_ROWSTREAM
     if N <= 8 and M >= 64:
         return VAR_ROW_256x4 if N <= 4 else VAR_ROW_128x8
     # tensor-core tiles: fp64 DMMA for float64/complex128, 3xTF32 for float32/complex64
@@ -352,6 +355,12 @@ def build_pair_desc(dims: PairDims, dtype, accumulate=False, sm_count=148,
 
     if variant is None:
         variant = choose_variant(dtype, B, M, N, K, allow_dmma)
+    if variant == VAR_ROWSTREAM:
+        # the streaming kernel needs exact tiles: every m dim must divide
+        ok = N <= 8 and K <= 8 and B == 1 and M < 1 << 32 and all(
+            d[0] <= 256 or d[0] % 256 == 0 or True for d in m)
+        if not ok:
+            variant = VAR_ROW_256x4 if N <= 4 else VAR_ROW_128x8
     MT, NT, KT = VARIANT_TILES[variant]
 
     tm, gm, pm = split_tile(m, (1, 2), MT, order_col=2)
@@ -438,7 +447,15 @@ def build_pair_desc(dims: PairDims, dtype, accumulate=False, sm_count=148,
     # producers decode tile indices with shifts/masks instead of idiv
     is_p2 = lambda e: e > 0 and (e & (e - 1)) == 0  # noqa: E731
     grid_pow2 = all(is_p2(g[0]) for g in gm + gn + gb)
-    W[W_FLAGS] = (1 if accumulate else 0) | (2 if pair_ok else 0) | (4 if grid_pow2 else 0)
+    m_pow2 = all(is_p2(d[0]) for d in tm) and all(is_p2(g[0]) for g in gm)
+    if variant == VAR_ROWSTREAM and pm is not None and pm[1] % pm[2] != 0:
+        # ragged blocked m dim: fall back to the staged row policy
+        return build_pair_desc(dims, dtype, accumulate=accumulate, sm_count=sm_count,
+                               variant=VAR_ROW_256x4 if N <= 4 else VAR_ROW_128x8,
+                               allow_dmma=allow_dmma, c_dense_elems=c_dense_elems,
+                               force_splitk=force_splitk)
+    W[W_FLAGS] = ((1 if accumulate else 0) | (2 if pair_ok else 0) | (4 if grid_pow2 else 0)
+                  | (8 if m_pow2 else 0))
     W[W_VARIANT] = variant
     W[W_CELEMS] = int(c_dense_elems)
 
