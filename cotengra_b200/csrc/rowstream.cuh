@@ -24,6 +24,10 @@ rowstream_kernel(const int64_t* __restrict__ D, const T* __restrict__ A, const T
   const int n_m = n_tm + n_gm;
   const bool accumulate = (D[W_FLAGS] & 1) != 0;
   const bool pair_ok = (D[W_FLAGS] & 2) != 0 && !accumulate && sizeof(T) == 16;
+  // 8-byte elements: bit4 = groups of four columns are adjacent and 32-byte aligned,
+  // bit5 = pairs of columns adjacent and 16-byte aligned -> 256-/128-bit row stores
+  [[maybe_unused]] const bool quad8 = (D[W_FLAGS] & 16) != 0 && !accumulate && sizeof(T) == 8;
+  [[maybe_unused]] const bool pair8 = (D[W_FLAGS] & 32) != 0 && !accumulate && sizeof(T) == 8;
   const bool pow2 = (D[W_FLAGS] & 8) != 0;  // every m dim (tile and grid) is a power of two
   // m dims in enumeration order: tile dims (dim 0 fastest) then grid dims
   for (int d = tid; d < n_m; d += blockDim.x) {
@@ -89,59 +93,98 @@ rowstream_kernel(const int64_t* __restrict__ D, const T* __restrict__ A, const T
 
   const unsigned long long M = (unsigned long long)D[W_MTA] * (unsigned long long)D[W_TILES_M];
   const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
-  for (unsigned long long m = (unsigned long long)blockIdx.x * blockDim.x + tid; m < M; m += stride) {
-    unsigned e = (unsigned)m;
-    long long oa = 0, oc = 0;
-    if (pow2) {
-      for (int d = 0; d < n_m; ++d) {
-        const unsigned ext = s_mext[d];
-        const unsigned dig = e & (ext - 1);
-        e >>= 31 - __clz(ext);
-        oa += (long long)dig * s_msA[d];
-        oc += (long long)dig * s_msC[d];
+  // rows per thread and iteration: narrow element types need more loads in flight
+  // per thread to cover HBM latency (Little's law at <= 24 resident warps / SM)
+  constexpr int R = sizeof(T) >= 16 ? 1 : 2;
+  for (unsigned long long m0 = (unsigned long long)blockIdx.x * blockDim.x + tid; m0 < M; m0 += stride * R) {
+    long long oa[R], oc[R];
+    bool live[R];
+#pragma unroll
+    for (int i = 0; i < R; ++i) {
+      const unsigned long long m = m0 + (unsigned long long)i * stride;
+      live[i] = m < M;
+      unsigned e = live[i] ? (unsigned)m : 0u;
+      long long xa = 0, xc = 0;
+      if (pow2) {
+        for (int d = 0; d < n_m; ++d) {
+          const unsigned ext = s_mext[d];
+          const unsigned dig = e & (ext - 1);
+          e >>= 31 - __clz(ext);
+          xa += (long long)dig * s_msA[d];
+          xc += (long long)dig * s_msC[d];
+        }
+      } else {
+        for (int d = 0; d < n_m; ++d) {
+          const unsigned ext = s_mext[d];
+          const unsigned dig = e % ext;
+          e /= ext;
+          xa += (long long)dig * s_msA[d];
+          xc += (long long)dig * s_msC[d];
+        }
       }
-    } else {
-      for (int d = 0; d < n_m; ++d) {
-        const unsigned ext = s_mext[d];
-        const unsigned dig = e % ext;
-        e /= ext;
-        oa += (long long)dig * s_msA[d];
-        oc += (long long)dig * s_msC[d];
-      }
+      oa[i] = xa;
+      oc[i] = xc;
     }
-    T acc[NMAX];
+    T a[R][KMAX];
 #pragma unroll
-    for (int c = 0; c < NMAX; ++c) acc[c] = zero_of<T>();
-    const T* pa = A + oa;
-    T a[KMAX];
+    for (int i = 0; i < R; ++i)
 #pragma unroll
-    for (int kk = 0; kk < KMAX; ++kk)
-      if (kk < K) a[kk] = pa[akoff[kk]];
+      for (int kk = 0; kk < KMAX; ++kk)
+        if (kk < K) a[i][kk] = A[oa[i] + akoff[kk]];
 #pragma unroll
-    for (int kk = 0; kk < KMAX; ++kk) {
-      if (kk < K) {
+    for (int i = 0; i < R; ++i) {
+      T acc[NMAX];
 #pragma unroll
-        for (int c = 0; c < NMAX; ++c) {
-          if constexpr (BREG) {
-            mac(acc[c], a[kk], breg[kk][c]);
-          } else {
-            if (c < N) mac(acc[c], a[kk], s_B[kk * NMAX + c]);
+      for (int c = 0; c < NMAX; ++c) acc[c] = zero_of<T>();
+#pragma unroll
+      for (int kk = 0; kk < KMAX; ++kk) {
+        if (kk < K) {
+#pragma unroll
+          for (int c = 0; c < NMAX; ++c) {
+            if constexpr (BREG) {
+              mac(acc[c], a[i][kk], breg[kk][c]);
+            } else {
+              if (c < N) mac(acc[c], a[i][kk], s_B[kk * NMAX + c]);
+            }
           }
         }
       }
-    }
-    T* pc = C + oc;
-    if (pair_ok) {
+      if (!live[i]) continue;
+      T* pc = C + oc[i];
+      if constexpr (sizeof(T) == 8) {
+        if (quad8) {
 #pragma unroll
-      for (int c = 0; c < NMAX; c += 2)
-        if (c < N) store_pair_of(pc + s_cnoff[c], acc[c], acc[c + 1]);
-    } else {
-#pragma unroll
-      for (int c = 0; c < NMAX; ++c)
-        if (c < N) {
-          T* p = pc + s_cnoff[c];
-          *p = accumulate ? add_of(*p, acc[c]) : acc[c];
+          for (int c = 0; c + 3 < NMAX; c += 4)
+            if (c < N) {
+              const unsigned long long* q = reinterpret_cast<const unsigned long long*>(&acc[c]);
+              asm volatile("st.global.v4.b64 [%0], {%1,%2,%3,%4};" ::"l"(pc + s_cnoff[c]), "l"(q[0]), "l"(q[1]),
+                           "l"(q[2]), "l"(q[3])
+                           : "memory");
+            }
+          continue;
         }
+        if (pair8) {
+#pragma unroll
+          for (int c = 0; c + 1 < NMAX; c += 2)
+            if (c < N) {
+              const unsigned long long* q = reinterpret_cast<const unsigned long long*>(&acc[c]);
+              asm volatile("st.global.v2.b64 [%0], {%1,%2};" ::"l"(pc + s_cnoff[c]), "l"(q[0]), "l"(q[1]) : "memory");
+            }
+          continue;
+        }
+      }
+      if (pair_ok) {
+#pragma unroll
+        for (int c = 0; c < NMAX; c += 2)
+          if (c < N) store_pair_of(pc + s_cnoff[c], acc[c], acc[c + 1]);
+      } else {
+#pragma unroll
+        for (int c = 0; c < NMAX; ++c)
+          if (c < N) {
+            T* p = pc + s_cnoff[c];
+            *p = accumulate ? add_of(*p, acc[c]) : acc[c];
+          }
+      }
     }
   }
 }

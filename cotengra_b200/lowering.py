@@ -454,8 +454,18 @@ def build_pair_desc(dims: PairDims, dtype, accumulate=False, sm_count=148,
                                variant=VAR_ROW_256x4 if N <= 4 else VAR_ROW_128x8,
                                allow_dmma=allow_dmma, c_dense_elems=c_dense_elems,
                                force_splitk=force_splitk)
+    # 8-byte element types: groups of 4 (bit4) / 2 (bit5) columns adjacent in C and
+    # 32- / 16-byte aligned -> vector row stores in the streaming row kernel
+    def _cols_ok(g):
+        return (
+            DTYPE_SIZES[dtype] == 8 and dense_n and pn is None and NTa % g == 0
+            and all(d[2] % g == 0 for d in tm)
+            and all(x[3] % g == 0 for x in gm) and all(x[3] % g == 0 for x in gn)
+            and all(x[4] % g == 0 for x in gb)
+        )
+
     W[W_FLAGS] = ((1 if accumulate else 0) | (2 if pair_ok else 0) | (4 if grid_pow2 else 0)
-                  | (8 if m_pow2 else 0))
+                  | (8 if m_pow2 else 0) | (16 if _cols_ok(4) else 0) | (32 if _cols_ok(2) else 0))
     W[W_VARIANT] = variant
     W[W_CELEMS] = int(c_dense_elems)
 
