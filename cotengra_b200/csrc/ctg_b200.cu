@@ -155,10 +155,38 @@ int launch_rowstream(const int64_t* h, const int64_t* d, const void* A, const vo
   return CTGB_OK;
 }
 
+// complex64 on tcgen05: prepare B' (hi/lo, tile order) once, then the warp-specialised kernel
+template <int NT, int STAGES>
+int launch_tc05(const int64_t* h, const int64_t* d, const void* A, const void* B, void* C, cudaStream_t st) {
+  using P = Tc05Policy<NT, STAGES>;
+  DevInfo& di = devinfo();
+  if (!di.ok) return fail(CTGB_E_CUDA, "no CUDA device");
+  auto exact = [&](int pg, int full, int text) { return h[pg] < 0 || (h[full] % h[text]) == 0; };
+  if (h[W_DTYPE] != CTGB_C64 || h[W_MTA] != 128 || h[W_NTA] != NT || h[W_KTA] != 16 ||
+      !exact(W_PGM, W_MFULL, W_MTEXT) || !exact(W_PGN, W_NFULL, W_NTEXT) || !exact(W_PGK, W_KFULL, W_KTEXT))
+    return fail(CTGB_E_VALUE, "descriptor does not fit the tcgen05 kernel");
+  const unsigned long long tiles = (unsigned long long)h[W_TILES_B] * h[W_TILES_N] * h[W_STEPS_K];
+  const size_t bytes = (size_t)tiles * P::PAIR_BYTES;
+  float* Bp = nullptr;
+  CUDA_TRY(cudaMallocAsync((void**)&Bp, bytes, st));
+  const unsigned long long total = tiles * P::TILE_FLOATS;
+  unsigned long long blocks = (total + 255) / 256;
+  if (blocks > (unsigned long long)di.sms * 8) blocks = (unsigned long long)di.sms * 8;
+  bprime_kernel<NT><<<(unsigned)blocks, 256, 0, st>>>(d, (const float2*)B, Bp);
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  int rc = launch_gett_policy<float2, P>(h, d, A, Bp, C, st);
+  cudaFreeAsync(Bp, st);
+  return rc;
+}
+
 template <typename T>
 int launch_gett_typed(const int64_t* h, const int64_t* d, const void* A, const void* B, void* C, cudaStream_t st) {
   const int variant = (int)h[W_VARIANT];
   if (variant == VAR_ROWSTREAM) return launch_rowstream<T>(h, d, A, B, C, st);
+  if constexpr (std::is_same<T, float2>::value) {
+    if (variant == VAR_TC05_128x64) return launch_tc05<64, 2>(h, d, A, B, C, st);
+    if (variant == VAR_TC05_128x32) return launch_tc05<32, 3>(h, d, A, B, C, st);
+  }
   switch (variant) {
     case VAR_SIMT_64x64: return launch_gett_policy<T, SimtPolicy<T, 64, 64, 8, 3>>(h, d, A, B, C, st);
     case VAR_KRED: return launch_gett_policy<T, KredPolicy<T, 1, 1, 512, 6>>(h, d, A, B, C, st);

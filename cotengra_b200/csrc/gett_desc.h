@@ -66,7 +66,9 @@ enum : int {
   VAR_DMMA_256x16 = 5,
   VAR_ROW_128x8 = 6,   // one output row per thread (HBM-bound skinny nodes), N <= 8
   VAR_ROW_256x4 = 7,   // same, N <= 4 (fewer registers -> more resident CTAs)
-  VAR_ROWSTREAM = 8    // N, K <= 8, exact tiles, no batch: thread-per-row straight from global memory
+  VAR_ROWSTREAM = 8,   // N, K <= 8, exact tiles, no batch: thread-per-row straight from global memory
+  VAR_TC05_128x64 = 9, // complex64, exact 128 x 64 x 16 tiles: tcgen05.mma kind::tf32 (3 passes), TMEM accumulators
+  VAR_TC05_128x32 = 10
 };
 
 // ---- single-operand descriptor (cotengra/contract.py:332-361) -------------

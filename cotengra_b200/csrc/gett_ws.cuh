@@ -68,8 +68,9 @@ struct BCacheOf<P, true> {
 
 template <class P>
 struct GettSmem {
-  static constexpr int NA = (P::A_ELEMS + PRODUCER_THREADS - 1) / PRODUCER_THREADS;
-  static constexpr int NB = (P::B_ELEMS + PRODUCER_THREADS - 1) / PRODUCER_THREADS;
+  // slots of the per-element gather tables (elements the producers fetch one by one)
+  static constexpr int NA = (P::A_GATHER + PRODUCER_THREADS - 1) / PRODUCER_THREADS;
+  static constexpr int NB = (P::B_GATHER + PRODUCER_THREADS - 1) / PRODUCER_THREADS;
   // tile-info ring.  STAGES + 2 slots: the producer decodes tile j+TI right after
   // issuing tile j+TI-1, whose first stage needed the "empty" arrival of every
   // consumer warp for tile j+1 -- i.e. all of them are past the epilogue of tile
@@ -82,13 +83,139 @@ struct GettSmem {
            + 8 * (size_t)(NA + NB) * PRODUCER_THREADS                                      // element deltas
            + 8 * (size_t)(P::MT + P::NT)                                                   // C offsets
            + 8 * (size_t)2 * KCHUNK                                                        // k-step bases
-           + 8 * (size_t)3 * TI                                                            // tile bases
+           + 8 * (size_t)4 * TI                                                            // tile bases
            + 8 * (size_t)2 * P::STAGES                                                     // mbarriers
            + 4 * (size_t)(NA + NB) * PRODUCER_THREADS                                      // element (r, kk)
            + 4 * (size_t)KCHUNK + 4 * (size_t)2 * TI                                       // valid counts
            + 64;
   }
 };
+
+// Consumer side of the tcgen05 policy (256 threads): A'lo generation, UMMA issue, TMEM epilogue.
+template <typename T, class P>
+__device__ __forceinline__ void tc05_consumer(const int64_t* __restrict__ D, T* __restrict__ C, T* sA, T* sB,
+                                              unsigned long long* bar_full, unsigned long long* bar_empty,
+                                              unsigned long long* bar_tile, unsigned* tmem_slot, const long long* ti_base,
+                                              const int* ti_valid, const long long* offMC, const long long* offNC,
+                                              unsigned nw, unsigned tiles_all, unsigned steps_k, unsigned steps_per_split,
+                                              bool accumulate, bool atomic) {
+  constexpr int MT = P::MT, NT = P::NT, STAGES = P::STAGES, NCONS = P::THREADS;
+  constexpr int TI = GettSmem<P>::TI;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const bool quad_ok = (D[W_FLAGS] & 16) != 0 && !accumulate && !atomic;
+  if (warp == 0) {
+    const unsigned a = (unsigned)__cvta_generic_to_shared(tmem_slot);
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"(a), "r"(P::TMEM_COLS)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
+  named_sync<2, NCONS>();
+  asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+  const unsigned taddr = *tmem_slot;
+  // InstrDescriptor: D=f32 [4,6)=1, A=tf32 [7,10)=2, B=tf32 [10,13)=2, K-major A/B, N>>3 [17,23), M>>4 [24,29)
+  constexpr unsigned idesc =
+      (1u << 4) | (2u << 7) | (2u << 10) | ((unsigned)(P::TMEM_COLS >> 3) << 17) | ((unsigned)(MT >> 4) << 24);
+  unsigned g = 0, tile_phase = 0;
+  for (unsigned j = 0; j < nw; ++j) {
+    const unsigned w = blockIdx.x + j * gridDim.x;
+    const unsigned ks = w / tiles_all;
+    const unsigned k0 = ks * steps_per_split, k1 = min(steps_k, k0 + steps_per_split);
+    for (unsigned step = k0; step < k1; ++step, ++g) {
+      const int st = (int)(g % STAGES);
+      mbar_wait(&bar_full[st], (g / STAGES) & 1);
+      // A'lo = A' - trunc_tf32(A') for the whole stage (same tile order)
+      float4* ah = reinterpret_cast<float4*>(sA + st * P::A_ELEMS);
+      float4* al = ah + (MT * P::KT) / 2;
+#pragma unroll
+      for (int i = tid; i < (MT * P::KT) / 2; i += NCONS) {
+        const float4 v = ah[i];
+        al[i] = make_float4(v.x - trunc_tf32(v.x), v.y - trunc_tf32(v.y), v.z - trunc_tf32(v.z), v.w - trunc_tf32(v.w));
+      }
+      asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");  // generic-proxy writes -> tensor core
+      asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
+      named_sync<2, NCONS>();
+      asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+      if (tid == 0) {
+        const unsigned a_hi = (unsigned)__cvta_generic_to_shared(ah);
+        const unsigned a_lo = (unsigned)__cvta_generic_to_shared(al);
+        const unsigned b_hi = (unsigned)__cvta_generic_to_shared(sB + st * P::B_ELEMS);
+        const unsigned b_lo = b_hi + P::TILE_FLOATS * 4;
+#pragma unroll
+        for (int pass = 0; pass < 3; ++pass) {
+          const unsigned a0 = pass == 0 ? a_lo : a_hi, b0 = pass == 1 ? b_lo : b_hi;  // lo*hi, hi*lo, hi*hi
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            // one UMMA eats K = 8 floats = 2 chunks; chunk stride (LBO) = rows*16 B, 8-row group stride (SBO) = 128 B
+            const uint64_t da = umma_desc_kmajor(a0 + q * 2 * MT * 16, MT * 16, 128);
+            const uint64_t db = umma_desc_kmajor(b0 + q * 2 * (2 * NT) * 16, (2 * NT) * 16, 128);
+            const unsigned acc = (step != k0 || pass != 0 || q != 0) ? 1u : 0u;
+            asm volatile(
+                "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(taddr),
+                "l"(da), "l"(db), "r"(idesc), "r"(acc)
+                : "memory");
+          }
+        }
+        // the stage may be refilled once these UMMAs have read it
+        const unsigned mb = (unsigned)__cvta_generic_to_shared(&bar_empty[st]);
+        asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n" ::"r"(mb) : "memory");
+      }
+    }
+    // ---- tile done: wait for the accumulator, then TMEM -> registers -> C
+    if (tid == 0) {
+      const unsigned mb = (unsigned)__cvta_generic_to_shared(bar_tile);
+      asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n" ::"r"(mb) : "memory");
+    }
+    mbar_wait(bar_tile, tile_phase);
+    tile_phase ^= 1;
+    asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+    const int slot = (int)(j % TI);
+    const long long baseC = ti_base[slot * 4 + 2];
+    const int m_valid = ti_valid[slot * 2 + 0], n_valid = ti_valid[slot * 2 + 1];
+    const int quad = warp & 3, half = warp >> 2;  // TMEM lane quadrant, column half
+    const int r = quad * 32 + lane;
+    T* crow = C + baseC + offMC[r];
+#pragma unroll 4
+    for (int cc = 0; cc < NT; cc += 8) {
+      const int col = half * NT + cc;  // fp32 column; complex column = col / 2
+      unsigned v[8];
+      const unsigned ta = taddr + ((unsigned)(quad * 32) << 16) + (unsigned)col;
+      asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];\n"
+                   : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
+                   : "r"(ta));
+      asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
+      const int c0 = col >> 1;
+      if (r < m_valid && c0 < n_valid) {
+        if (quad_ok) {
+          const unsigned long long q0 = ((unsigned long long)v[1] << 32) | v[0], q1 = ((unsigned long long)v[3] << 32) | v[2];
+          const unsigned long long q2 = ((unsigned long long)v[5] << 32) | v[4], q3 = ((unsigned long long)v[7] << 32) | v[6];
+          asm volatile("st.global.v4.b64 [%0], {%1,%2,%3,%4};\n" ::"l"(crow + offNC[c0]), "l"(q0), "l"(q1), "l"(q2), "l"(q3)
+                       : "memory");
+        } else {
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            if (c0 + e < n_valid) {
+              T* p = crow + offNC[c0 + e];
+              const T val = make_float2(__uint_as_float(v[2 * e]), __uint_as_float(v[2 * e + 1]));
+              if (atomic) {
+                atomic_add_of(p, val);
+              } else if (accumulate) {
+                *p = add_of(*p, val);
+              } else {
+                *p = val;
+              }
+            }
+          }
+        }
+      }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
+  }
+  named_sync<2, NCONS>();
+  if (warp == 0)
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(taddr), "r"(P::TMEM_COLS) : "memory");
+}
 
 template <typename T, class P>
 __global__ void __launch_bounds__(P::THREADS + PRODUCER_THREADS, P::MIN_BLOCKS)
@@ -106,13 +233,18 @@ gett_kernel(const int64_t* __restrict__ D, const T* __restrict__ A, const T* __r
   long long* offNC = offMC + MT;
   long long* kbA = offNC + NT;
   long long* kbB = kbA + KCHUNK;
-  long long* ti_base = kbB + KCHUNK;  // [TI][3]: A, B, C
-  unsigned long long* bar_full = reinterpret_cast<unsigned long long*>(ti_base + 3 * TI);
+  long long* ti_base = kbB + KCHUNK;  // [TI][4]: A, B, C, B'-tile index
+  unsigned long long* bar_full = reinterpret_cast<unsigned long long*>(ti_base + 4 * TI);
   unsigned long long* bar_empty = bar_full + STAGES;
   unsigned* metaA = reinterpret_cast<unsigned*>(bar_empty + STAGES);
   unsigned* metaB = metaA + NA * NPROD;
   int* kval = reinterpret_cast<int*>(metaB + NB * NPROD);
   int* ti_valid = kval + KCHUNK;  // [TI][2]: m_valid, n_valid
+
+  __shared__ __align__(8) unsigned long long bar_tile_storage;
+  __shared__ unsigned tmem_slot_storage;
+  [[maybe_unused]] unsigned long long* bar_tile = &bar_tile_storage;
+  [[maybe_unused]] unsigned* tmem_slot = &tmem_slot_storage;
 
   const int tid = threadIdx.x;
   const int lane = tid & 31;
@@ -161,8 +293,9 @@ gett_kernel(const int64_t* __restrict__ D, const T* __restrict__ A, const T* __r
   if (tid == 0) {
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(&bar_full[s], NPROD);
-      mbar_init(&bar_empty[s], NCONS / 32);
+      mbar_init(&bar_empty[s], P::IS_TC05 ? 1 : NCONS / 32);  // tc05: one tcgen05.commit per stage
     }
+    if constexpr (P::IS_TC05) mbar_init(bar_tile, 1);
     asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
   }
   if (is_producer) {
@@ -322,16 +455,18 @@ gett_kernel(const int64_t* __restrict__ D, const T* __restrict__ A, const T* __r
         vm = warp_sum_i(vm);
         vn = warp_sum_i(vn);
         if (lane == 0) {
-          ti_base[slot * 3 + 0] = a;
-          ti_base[slot * 3 + 1] = b;
-          ti_base[slot * 3 + 2] = c;
+          ti_base[slot * 4 + 0] = a;
+          ti_base[slot * 4 + 1] = b;
+          ti_base[slot * 4 + 2] = c;
+          ti_base[slot * 4 + 3] = (long long)ib_ * tiles_n + in_;
           ti_valid[slot * 2 + 0] = pgm < 0 ? MTa : vm;
           ti_valid[slot * 2 + 1] = pgn < 0 ? NTa : vn;
           __threadfence_block();
         }
       }
       named_sync<1, NPROD>();
-      const long long tA = ti_base[slot * 3 + 0], tB = ti_base[slot * 3 + 1];
+      const long long tA = ti_base[slot * 4 + 0], tB = ti_base[slot * 4 + 1];
+      [[maybe_unused]] const long long tBp = ti_base[slot * 4 + 3];
       const unsigned m_valid = (unsigned)ti_valid[slot * 2 + 0], n_valid = (unsigned)ti_valid[slot * 2 + 1];
 
       for (unsigned step = k0; step < k1; ++step, ++g) {
@@ -374,7 +509,21 @@ gett_kernel(const int64_t* __restrict__ D, const T* __restrict__ A, const T* __r
             }
           }
         }
-        if (exactB) {
+        if constexpr (P::IS_TC05) {
+          // the stage's B'hi + B'lo tiles are contiguous in the prepared buffer: one TMA bulk copy
+          if (ptid == 0) {
+            const unsigned bar = (unsigned)__cvta_generic_to_shared(&bar_full[st]);
+            const unsigned dst = (unsigned)__cvta_generic_to_shared(dB);
+            const char* src = reinterpret_cast<const char*>(B) +
+                              ((unsigned long long)tBp * steps_k + step) * (unsigned long long)P::PAIR_BYTES;
+            asm volatile("mbarrier.expect_tx.relaxed.cta.shared::cta.b64 [%0], %1;\n" ::"r"(bar), "r"(P::PAIR_BYTES)
+                         : "memory");
+            asm volatile(
+                "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::"r"(dst),
+                "l"(src), "r"(P::PAIR_BYTES), "r"(bar)
+                : "memory");
+          }
+        } else if (exactB) {
 #pragma unroll
           for (int i = 0; i < NB; ++i) {
             const unsigned meta = metaB[i * NPROD + ptid];
@@ -398,6 +547,11 @@ gett_kernel(const int64_t* __restrict__ D, const T* __restrict__ A, const T* __r
     cp_async_wait<0>();  // do not exit with copies in flight
   } else {
     // ===================================================== CONSUMER WARPS
+    if constexpr (P::IS_TC05) {
+      tc05_consumer<T, P>(D, C, sA, sB, bar_full, bar_empty, bar_tile, tmem_slot, ti_base, ti_valid, offMC, offNC, nw,
+                          tiles_all, steps_k, steps_per_split, accumulate, atomic);
+      return;
+    }
     if constexpr (P::CONSUMER_REGS > 0) reg_alloc<P::CONSUMER_REGS>();
     // valid k of a step: only a blocked (partial) k dim can shorten it
     const unsigned pk_div = pgk >= 0 ? (unsigned)D[OFF_GK + pgk * 4 + 1] : 1u;
@@ -438,7 +592,7 @@ gett_kernel(const int64_t* __restrict__ D, const T* __restrict__ A, const T* __r
       }
       // ---- epilogue of tile j: store in the parent's index order (strided C)
       const int slot = (int)(j % TI);
-      const long long baseC = ti_base[slot * 3 + 2];
+      const long long baseC = ti_base[slot * 4 + 2];
       const int m_valid = ti_valid[slot * 2 + 0], n_valid = ti_valid[slot * 2 + 1];
       P::epilogue(
           acc, scratch,

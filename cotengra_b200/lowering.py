@@ -58,6 +58,7 @@ SDESC_MAGIC = 0x4354474253303031
 
 VAR_SIMT_64x64, VAR_KRED, VAR_DMMA_128x64, VAR_DMMA_64x128, VAR_DMMA_256x32 = 0, 1, 2, 3, 4
 VAR_DMMA_256x16, VAR_ROW_128x8, VAR_ROW_256x4, VAR_ROWSTREAM = 5, 6, 7, 8
+VAR_TC05_128x64, VAR_TC05_128x32 = 9, 10
 # (MT, NT, KT) of every kernel variant -- must match ctg_b200.cu's dispatch
 VARIANT_TILES = {
     VAR_SIMT_64x64: (64, 64, 8),
@@ -69,6 +70,8 @@ VARIANT_TILES = {
     VAR_ROW_128x8: (256, 8, 4),
     VAR_ROW_256x4: (256, 4, 4),
     VAR_ROWSTREAM: (256, 8, 8),
+    VAR_TC05_128x64: (128, 64, 16),
+    VAR_TC05_128x32: (128, 32, 16),
 }
 
 DTYPE_CODES = {"float32": 0, "float64": 1, "complex64": 2, "complex128": 3}
@@ -315,13 +318,20 @@ class PairPlan:
     splitk: int
 
 
-def choose_variant(dtype, B, M, N, K, allow_dmma=True, allow_stream=True):
+def choose_variant(dtype, B, M, N, K, allow_dmma=True, allow_stream=True, allow_tc05=True):
     if M == 1 and N == 1 and B == 1 and K >= 8192:
         return VAR_KRED
     if N <= 8 and K <= 8 and B == 1 and 64 <= M < 1 << 32 and allow_stream:
         return VAR_ROWSTREAM
     if N <= 8 and M >= 64:
         return VAR_ROW_256x4 if N <= 4 else VAR_ROW_128x8
+    # complex64 dense nodes with exact power-of-two tiles: tcgen05 (kind::tf32 x3, TMEM)
+    if (allow_dmma and allow_tc05 and dtype == "complex64" and M % 128 == 0 and K % 16 == 0
+            and K <= 256 and M * N * K >= 1 << 20):
+        if N % 64 == 0:
+            return VAR_TC05_128x64
+        if N == 32:
+            return VAR_TC05_128x32
     # tensor-core tiles: fp64 DMMA for float64/complex128, 3xTF32 for float32/complex64
     if allow_dmma and M * N * K >= 1 << 15 and M * N >= 1024:
         if N >= 96:
@@ -448,6 +458,15 @@ def build_pair_desc(dims: PairDims, dtype, accumulate=False, sm_count=148,
     is_p2 = lambda e: e > 0 and (e & (e - 1)) == 0  # noqa: E731
     grid_pow2 = all(is_p2(g[0]) for g in gm + gn + gb)
     m_pow2 = all(is_p2(d[0]) for d in tm) and all(is_p2(g[0]) for g in gm)
+    if variant in (VAR_TC05_128x64, VAR_TC05_128x32):
+        # the tcgen05 kernel only takes exact tiles of its native shape
+        exact = (MTa, NTa, KTa) == (MT, NT, KT) and dtype == "complex64" and all(
+            p is None or p[1] % p[2] == 0 for p in (pm, pn, pk))
+        if not exact:
+            fb = choose_variant(dtype, B, M, N, K, allow_dmma, allow_tc05=False)
+            return build_pair_desc(dims, dtype, accumulate=accumulate, sm_count=sm_count, variant=fb,
+                                   allow_dmma=allow_dmma, c_dense_elems=c_dense_elems,
+                                   force_splitk=force_splitk)
     if variant == VAR_ROWSTREAM and pm is not None and pm[1] % pm[2] != 0:
         # ragged blocked m dim: fall back to the staged row policy
         return build_pair_desc(dims, dtype, accumulate=accumulate, sm_count=sm_count,

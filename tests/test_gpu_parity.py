@@ -105,7 +105,7 @@ def test_tensordot_golden_shapes():
 
 
 @pytest.mark.parametrize("variant", [L.VAR_SIMT_64x64, L.VAR_DMMA_128x64, L.VAR_DMMA_64x128,
-                                     L.VAR_DMMA_256x32, L.VAR_DMMA_256x16, L.VAR_ROW_128x8, L.VAR_ROW_256x4, L.VAR_ROWSTREAM])
+                                     L.VAR_DMMA_256x32, L.VAR_DMMA_256x16, L.VAR_ROW_128x8, L.VAR_ROW_256x4, L.VAR_ROWSTREAM, L.VAR_TC05_128x64, L.VAR_TC05_128x32])
 @pytest.mark.parametrize("dtype", ["complex128", "float64", "complex64", "float32"])
 def test_every_kernel_variant_ragged_gemm(variant, dtype):
     import torch
