@@ -76,7 +76,8 @@ struct GettSmem {
   // consumer warp for tile j+1 -- i.e. all of them are past the epilogue of tile
   // j, the last reader of slot j % TI.  (STAGES + 1 is one too few: the decode
   // runs BEFORE the producer waits on the stage it will fill.)
-  static constexpr int TI = P::STAGES + 2;
+  // (the tcgen05 policy's epilogue group may lag one more tile behind: two TMEM accumulators)
+  static constexpr int TI = P::STAGES + (P::IS_TC05 ? 4 : 2);
   template <typename T>
   static constexpr size_t bytes() {
     return sizeof(T) * ((size_t)P::STAGES * (P::A_ELEMS + P::B_ELEMS) + P::SCRATCH_ELEMS)  // ring + scratch
@@ -91,21 +92,27 @@ struct GettSmem {
   }
 };
 
-// Consumer side of the tcgen05 policy (256 threads): A'lo generation, UMMA issue, TMEM epilogue.
+// Consumer side of the tcgen05 policy, itself specialised:
+//   warps 0-3  "MMA group": build A'lo for the stage, issue the 12 UMMAs (one elected
+//              thread), commit them to the stage's "empty" barrier;
+//   warps 4-7  "epilogue group": TMEM -> registers -> C for the previous tile while the
+//              MMA group already works on the next one (two TMEM accumulators).
 template <typename T, class P>
 __device__ __forceinline__ void tc05_consumer(const int64_t* __restrict__ D, T* __restrict__ C, T* sA, T* sB,
                                               unsigned long long* bar_full, unsigned long long* bar_empty,
-                                              unsigned long long* bar_tile, unsigned* tmem_slot, const long long* ti_base,
+                                              unsigned long long* bar_tmem, unsigned* tmem_slot, const long long* ti_base,
                                               const int* ti_valid, const long long* offMC, const long long* offNC,
                                               unsigned nw, unsigned tiles_all, unsigned steps_k, unsigned steps_per_split,
                                               bool accumulate, bool atomic) {
   constexpr int MT = P::MT, NT = P::NT, STAGES = P::STAGES, NCONS = P::THREADS;
   constexpr int TI = GettSmem<P>::TI;
+  constexpr int GROUP = 128;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const bool quad_ok = (D[W_FLAGS] & 16) != 0 && !accumulate && !atomic;
+  unsigned long long* tmem_full = bar_tmem;       // [2] count 1 (tcgen05.commit)
+  unsigned long long* tmem_empty = bar_tmem + 2;  // [2] count 4 (epilogue warps)
   if (warp == 0) {
     const unsigned a = (unsigned)__cvta_generic_to_shared(tmem_slot);
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"(a), "r"(P::TMEM_COLS)
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"(a), "r"(2 * P::TMEM_COLS)
                  : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n" ::: "memory");
   }
@@ -116,105 +123,122 @@ __device__ __forceinline__ void tc05_consumer(const int64_t* __restrict__ D, T* 
   // InstrDescriptor: D=f32 [4,6)=1, A=tf32 [7,10)=2, B=tf32 [10,13)=2, K-major A/B, N>>3 [17,23), M>>4 [24,29)
   constexpr unsigned idesc =
       (1u << 4) | (2u << 7) | (2u << 10) | ((unsigned)(P::TMEM_COLS >> 3) << 17) | ((unsigned)(MT >> 4) << 24);
-  unsigned g = 0, tile_phase = 0;
-  for (unsigned j = 0; j < nw; ++j) {
-    const unsigned w = blockIdx.x + j * gridDim.x;
-    const unsigned ks = w / tiles_all;
-    const unsigned k0 = ks * steps_per_split, k1 = min(steps_k, k0 + steps_per_split);
-    for (unsigned step = k0; step < k1; ++step, ++g) {
-      const int st = (int)(g % STAGES);
-      mbar_wait(&bar_full[st], (g / STAGES) & 1);
-      // A'lo = A' - trunc_tf32(A') for the whole stage (same tile order)
-      float4* ah = reinterpret_cast<float4*>(sA + st * P::A_ELEMS);
-      float4* al = ah + (MT * P::KT) / 2;
-#pragma unroll
-      for (int i = tid; i < (MT * P::KT) / 2; i += NCONS) {
-        const float4 v = ah[i];
-        al[i] = make_float4(v.x - trunc_tf32(v.x), v.y - trunc_tf32(v.y), v.z - trunc_tf32(v.z), v.w - trunc_tf32(v.w));
-      }
-      asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");  // generic-proxy writes -> tensor core
-      asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
-      named_sync<2, NCONS>();
+
+  if (warp < 4) {
+    // ------------------------------------------------------------ MMA group
+    unsigned g = 0;
+    for (unsigned j = 0; j < nw; ++j) {
+      const unsigned w = blockIdx.x + j * gridDim.x;
+      const unsigned ks = w / tiles_all;
+      const unsigned k0 = ks * steps_per_split, k1 = min(steps_k, k0 + steps_per_split);
+      const unsigned buf = j & 1;
+      mbar_wait(&tmem_empty[buf], ((j >> 1) & 1) ^ 1);  // epilogue of tile j-2 has drained this accumulator
       asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
-      if (tid == 0) {
-        const unsigned a_hi = (unsigned)__cvta_generic_to_shared(ah);
-        const unsigned a_lo = (unsigned)__cvta_generic_to_shared(al);
-        const unsigned b_hi = (unsigned)__cvta_generic_to_shared(sB + st * P::B_ELEMS);
-        const unsigned b_lo = b_hi + P::TILE_FLOATS * 4;
+      for (unsigned step = k0; step < k1; ++step, ++g) {
+        const int st = (int)(g % STAGES);
+        mbar_wait(&bar_full[st], (g / STAGES) & 1);
+        // A'lo = A' - trunc_tf32(A') for the whole stage (same tile order)
+        float4* ah = reinterpret_cast<float4*>(sA + st * P::A_ELEMS);
+        float4* al = ah + (MT * P::KT) / 2;
 #pragma unroll
-        for (int pass = 0; pass < 3; ++pass) {
-          const unsigned a0 = pass == 0 ? a_lo : a_hi, b0 = pass == 1 ? b_lo : b_hi;  // lo*hi, hi*lo, hi*hi
+        for (int i = tid; i < (MT * P::KT) / 2; i += GROUP) {
+          const float4 v = ah[i];
+          al[i] = make_float4(v.x - trunc_tf32(v.x), v.y - trunc_tf32(v.y), v.z - trunc_tf32(v.z), v.w - trunc_tf32(v.w));
+        }
+        asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");  // generic-proxy writes -> tensor core
+        asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
+        named_sync<3, GROUP>();
+        asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+        if (tid == 0) {
+          const unsigned a_hi = (unsigned)__cvta_generic_to_shared(ah);
+          const unsigned a_lo = (unsigned)__cvta_generic_to_shared(al);
+          const unsigned b_hi = (unsigned)__cvta_generic_to_shared(sB + st * P::B_ELEMS);
+          const unsigned b_lo = b_hi + P::TILE_FLOATS * 4;
+          const unsigned dcol = taddr + buf * P::TMEM_COLS;
 #pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            // one UMMA eats K = 8 floats = 2 chunks; chunk stride (LBO) = rows*16 B, 8-row group stride (SBO) = 128 B
-            const uint64_t da = umma_desc_kmajor(a0 + q * 2 * MT * 16, MT * 16, 128);
-            const uint64_t db = umma_desc_kmajor(b0 + q * 2 * (2 * NT) * 16, (2 * NT) * 16, 128);
-            const unsigned acc = (step != k0 || pass != 0 || q != 0) ? 1u : 0u;
-            asm volatile(
-                "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-                "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(taddr),
-                "l"(da), "l"(db), "r"(idesc), "r"(acc)
-                : "memory");
+          for (int pass = 0; pass < 3; ++pass) {
+            const unsigned a0 = pass == 0 ? a_lo : a_hi, b0 = pass == 1 ? b_lo : b_hi;  // lo*hi, hi*lo, hi*hi
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              // one UMMA eats K = 8 floats = 2 chunks; chunk stride (LBO) = rows*16 B, 8-row group stride (SBO) = 128 B
+              const uint64_t da = umma_desc_kmajor(a0 + q * 2 * MT * 16, MT * 16, 128);
+              const uint64_t db = umma_desc_kmajor(b0 + q * 2 * (2 * NT) * 16, (2 * NT) * 16, 128);
+              const unsigned acc = (step != k0 || pass != 0 || q != 0) ? 1u : 0u;
+              asm volatile(
+                  "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                  "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(dcol),
+                  "l"(da), "l"(db), "r"(idesc), "r"(acc)
+                  : "memory");
+            }
+          }
+          // the stage may be refilled once these UMMAs have read it
+          const unsigned mb = (unsigned)__cvta_generic_to_shared(&bar_empty[st]);
+          asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n" ::"r"(mb)
+                       : "memory");
+          if (step + 1 == k1) {
+            const unsigned mf = (unsigned)__cvta_generic_to_shared(&tmem_full[buf]);
+            asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n" ::"r"(mf)
+                         : "memory");
           }
         }
-        // the stage may be refilled once these UMMAs have read it
-        const unsigned mb = (unsigned)__cvta_generic_to_shared(&bar_empty[st]);
-        asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n" ::"r"(mb) : "memory");
       }
     }
-    // ---- tile done: wait for the accumulator, then TMEM -> registers -> C
-    if (tid == 0) {
-      const unsigned mb = (unsigned)__cvta_generic_to_shared(bar_tile);
-      asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n" ::"r"(mb) : "memory");
-    }
-    mbar_wait(bar_tile, tile_phase);
-    tile_phase ^= 1;
-    asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
-    const int slot = (int)(j % TI);
-    const long long baseC = ti_base[slot * 4 + 2];
-    const int m_valid = ti_valid[slot * 2 + 0], n_valid = ti_valid[slot * 2 + 1];
-    const int quad = warp & 3, half = warp >> 2;  // TMEM lane quadrant, column half
+  } else {
+    // ------------------------------------------------------------ epilogue group
+    const bool quad_ok = (D[W_FLAGS] & 16) != 0 && !accumulate && !atomic;
+    const int quad = warp & 3;  // TMEM lane quadrant of this warp
     const int r = quad * 32 + lane;
-    T* crow = C + baseC + offMC[r];
+    for (unsigned j = 0; j < nw; ++j) {
+      const unsigned buf = j & 1;
+      mbar_wait(&tmem_full[buf], (j >> 1) & 1);
+      asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+      const int slot = (int)(j % TI);
+      const long long baseC = ti_base[slot * 4 + 2];
+      const int m_valid = ti_valid[slot * 2 + 0], n_valid = ti_valid[slot * 2 + 1];
+      T* crow = C + baseC + offMC[r];
 #pragma unroll 4
-    for (int cc = 0; cc < NT; cc += 8) {
-      const int col = half * NT + cc;  // fp32 column; complex column = col / 2
-      unsigned v[8];
-      const unsigned ta = taddr + ((unsigned)(quad * 32) << 16) + (unsigned)col;
-      asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];\n"
-                   : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
-                   : "r"(ta));
-      asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
-      const int c0 = col >> 1;
-      if (r < m_valid && c0 < n_valid) {
-        if (quad_ok) {
-          const unsigned long long q0 = ((unsigned long long)v[1] << 32) | v[0], q1 = ((unsigned long long)v[3] << 32) | v[2];
-          const unsigned long long q2 = ((unsigned long long)v[5] << 32) | v[4], q3 = ((unsigned long long)v[7] << 32) | v[6];
-          asm volatile("st.global.v4.b64 [%0], {%1,%2,%3,%4};\n" ::"l"(crow + offNC[c0]), "l"(q0), "l"(q1), "l"(q2), "l"(q3)
-                       : "memory");
-        } else {
+      for (int col = 0; col < 2 * NT; col += 8) {  // fp32 column; complex column = col / 2
+        unsigned v[8];
+        const unsigned ta = taddr + buf * P::TMEM_COLS + ((unsigned)(quad * 32) << 16) + (unsigned)col;
+        asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];\n"
+                     : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
+                     : "r"(ta));
+        asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
+        const int c0 = col >> 1;
+        if (r < m_valid && c0 < n_valid) {
+          if (quad_ok) {
+            const unsigned long long q0 = ((unsigned long long)v[1] << 32) | v[0], q1 = ((unsigned long long)v[3] << 32) | v[2];
+            const unsigned long long q2 = ((unsigned long long)v[5] << 32) | v[4], q3 = ((unsigned long long)v[7] << 32) | v[6];
+            asm volatile("st.global.v4.b64 [%0], {%1,%2,%3,%4};\n" ::"l"(crow + offNC[c0]), "l"(q0), "l"(q1), "l"(q2),
+                         "l"(q3)
+                         : "memory");
+          } else {
 #pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            if (c0 + e < n_valid) {
-              T* p = crow + offNC[c0 + e];
-              const T val = make_float2(__uint_as_float(v[2 * e]), __uint_as_float(v[2 * e + 1]));
-              if (atomic) {
-                atomic_add_of(p, val);
-              } else if (accumulate) {
-                *p = add_of(*p, val);
-              } else {
-                *p = val;
+            for (int e = 0; e < 4; ++e) {
+              if (c0 + e < n_valid) {
+                T* p = crow + offNC[c0 + e];
+                const T val = make_float2(__uint_as_float(v[2 * e]), __uint_as_float(v[2 * e + 1]));
+                if (atomic) {
+                  atomic_add_of(p, val);
+                } else if (accumulate) {
+                  *p = add_of(*p, val);
+                } else {
+                  *p = val;
+                }
               }
             }
           }
         }
       }
+      asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tmem_empty[buf]);
     }
-    asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
   }
   named_sync<2, NCONS>();
   if (warp == 0)
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(taddr), "r"(P::TMEM_COLS) : "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(taddr), "r"(2 * P::TMEM_COLS)
+                 : "memory");
 }
 
 template <typename T, class P>
@@ -241,9 +265,9 @@ gett_kernel(const int64_t* __restrict__ D, const T* __restrict__ A, const T* __r
   int* kval = reinterpret_cast<int*>(metaB + NB * NPROD);
   int* ti_valid = kval + KCHUNK;  // [TI][2]: m_valid, n_valid
 
-  __shared__ __align__(8) unsigned long long bar_tile_storage;
+  __shared__ __align__(8) unsigned long long bar_tile_storage[4];  // tc05: tmem_full[2], tmem_empty[2]
   __shared__ unsigned tmem_slot_storage;
-  [[maybe_unused]] unsigned long long* bar_tile = &bar_tile_storage;
+  [[maybe_unused]] unsigned long long* bar_tile = bar_tile_storage;
   [[maybe_unused]] unsigned* tmem_slot = &tmem_slot_storage;
 
   const int tid = threadIdx.x;
@@ -295,7 +319,12 @@ gett_kernel(const int64_t* __restrict__ D, const T* __restrict__ A, const T* __r
       mbar_init(&bar_full[s], NPROD);
       mbar_init(&bar_empty[s], P::IS_TC05 ? 1 : NCONS / 32);  // tc05: one tcgen05.commit per stage
     }
-    if constexpr (P::IS_TC05) mbar_init(bar_tile, 1);
+    if constexpr (P::IS_TC05) {
+      mbar_init(&bar_tile[0], 1);
+      mbar_init(&bar_tile[1], 1);
+      mbar_init(&bar_tile[2], 4);
+      mbar_init(&bar_tile[3], 4);
+    }
     asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
   }
   if (is_producer) {

@@ -37,7 +37,7 @@ struct Tc05Policy {
   static constexpr bool HAS_BCACHE = false;
   static constexpr int MIN_BLOCKS = 1;
   static constexpr int TMEM_COLS = 2 * NT;                    // fp32 columns of the accumulator
-  static_assert(TMEM_COLS == 64 || TMEM_COLS == 128 || TMEM_COLS == 256, "TMEM allocation must be a power of two");
+  static_assert(TMEM_COLS == 64 || TMEM_COLS == 128, "two accumulators of TMEM_COLS columns must fit 512 and be a power of two");
   struct Acc {};
   // [chunk = k'/4][row][k'%4] floats == [kk/2][row][kk%2] complex elements
   __device__ static __forceinline__ int idxA(int r, int kk) { return ((kk >> 1) * MT + r) * 2 + (kk & 1); }
