@@ -184,8 +184,8 @@ int launch_gett_typed(const int64_t* h, const int64_t* d, const void* A, const v
   const int variant = (int)h[W_VARIANT];
   if (variant == VAR_ROWSTREAM) return launch_rowstream<T>(h, d, A, B, C, st);
   if constexpr (std::is_same<T, float2>::value) {
-    if (variant == VAR_TC05_128x64) return launch_tc05<64, 3>(h, d, A, B, C, st);
-    if (variant == VAR_TC05_128x32) return launch_tc05<32, 4>(h, d, A, B, C, st);
+    if (variant == VAR_TC05_128x64) return launch_tc05<64, 2>(h, d, A, B, C, st);
+    if (variant == VAR_TC05_128x32) return launch_tc05<32, 3>(h, d, A, B, C, st);
   }
   switch (variant) {
     case VAR_SIMT_64x64: return launch_gett_policy<T, SimtPolicy<T, 64, 64, 8, 3>>(h, d, A, B, C, st);

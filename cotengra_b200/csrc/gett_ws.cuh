@@ -103,7 +103,8 @@ __device__ __forceinline__ void tc05_consumer(const int64_t* __restrict__ D, T* 
                                               unsigned long long* bar_tmem, unsigned* tmem_slot, const long long* ti_base,
                                               const int* ti_valid, const long long* offMC, const long long* offNC,
                                               unsigned nw, unsigned tiles_all, unsigned steps_k, unsigned steps_per_split,
-                                              bool accumulate, bool atomic) {
+                                              bool accumulate, bool atomic, const unsigned* metaA, bool bulk_a,
+                                              bool exactA) {
   constexpr int MT = P::MT, NT = P::NT, STAGES = P::STAGES, NCONS = P::THREADS;
   constexpr int TI = GettSmem<P>::TI;
   constexpr int GROUP = 128;
@@ -140,10 +141,26 @@ __device__ __forceinline__ void tc05_consumer(const int64_t* __restrict__ D, T* 
         // A'lo = A' - trunc_tf32(A') for the whole stage (same tile order)
         float4* ah = reinterpret_cast<float4*>(sA + st * P::A_ELEMS);
         float4* al = ah + (MT * P::KT) / 2;
+        if (bulk_a) {
+          // staging holds the tile in A-memory order; metaA[e] is the UMMA index of element e
+          const float2* stg = reinterpret_cast<const float2*>(al + (MT * P::KT) / 2);
+          float2* hi2 = reinterpret_cast<float2*>(ah);
+          float2* lo2 = reinterpret_cast<float2*>(al);
+#pragma unroll 4
+          for (int e = tid; e < MT * P::KT; e += GROUP) {
+            const float2 v = stg[e];
+            // (tables of launches with a blocked dim hold (r, kk) pairs instead of the index)
+            const unsigned meta = metaA[e];
+            const unsigned u = exactA ? meta : (unsigned)P::idxA((int)(meta & 0xFFFFu), (int)(meta >> 16));
+            hi2[u] = v;
+            lo2[u] = make_float2(v.x - trunc_tf32(v.x), v.y - trunc_tf32(v.y));
+          }
+        } else {
 #pragma unroll
-        for (int i = tid; i < (MT * P::KT) / 2; i += GROUP) {
-          const float4 v = ah[i];
-          al[i] = make_float4(v.x - trunc_tf32(v.x), v.y - trunc_tf32(v.y), v.z - trunc_tf32(v.z), v.w - trunc_tf32(v.w));
+          for (int i = tid; i < (MT * P::KT) / 2; i += GROUP) {
+            const float4 v = ah[i];
+            al[i] = make_float4(v.x - trunc_tf32(v.x), v.y - trunc_tf32(v.y), v.z - trunc_tf32(v.z), v.w - trunc_tf32(v.w));
+          }
         }
         asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");  // generic-proxy writes -> tensor core
         asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
@@ -292,6 +309,10 @@ gett_kernel(const int64_t* __restrict__ D, const T* __restrict__ A, const T* __r
   auto digit_of = [&](unsigned idx, unsigned div, unsigned ext) -> unsigned {
     return g_pow2 ? ((idx >> (31 - __clz(div))) & (ext - 1)) : ((idx / div) % ext);
   };
+  // tcgen05 policy: A tile = contiguous runs of run_a elements fetched by TMA bulk copies (flags bit6)
+  [[maybe_unused]] const bool bulk_a =
+      P::IS_TC05 && (D[W_FLAGS] & 64) != 0 && (reinterpret_cast<unsigned long long>(A) & 15ull) == 0;
+  [[maybe_unused]] const unsigned run_a = (unsigned)D[W_RUNA];
   // no blocked (partial) dim touches the operand: every tabulated element is always valid
   const bool exactA = pgm < 0 && pgk < 0, exactB = pgn < 0 && pgk < 0;
 
@@ -521,7 +542,31 @@ gett_kernel(const int64_t* __restrict__ D, const T* __restrict__ A, const T* __r
         const T* srcA = A + tA + kbA[ti];
         const T* srcB = B + tB + kbB[ti];
         const unsigned kv = (unsigned)kval[ti];
-        if (exactA) {
+        bool arrived = false;
+        if constexpr (P::IS_TC05) {
+          if (bulk_a) {
+            // the A tile is a set of long contiguous runs: TMA bulk copies into the staging
+            // area (memory order); the MMA group scatters them into the UMMA layout
+            const unsigned bar = (unsigned)__cvta_generic_to_shared(&bar_full[st]);
+            const unsigned nruns = (unsigned)(MTa * KTa) / run_a;
+            const unsigned mine = ptid < nruns ? (nruns - ptid + NPROD - 1) / NPROD : 0u;
+            const unsigned bytes = mine * run_a * (unsigned)sizeof(T) + (ptid == 0 ? (unsigned)P::PAIR_BYTES : 0u);
+            asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.expect_tx.shared::cta.b64 st, [%0], %1;\n\t}\n" ::"r"(bar),
+                         "r"(bytes)
+                         : "memory");
+            T* stg = dA + 2 * P::MT * P::KT;
+            for (unsigned q = ptid; q < nruns; q += NPROD) {
+              const unsigned dst = (unsigned)__cvta_generic_to_shared(stg + q * run_a);
+              asm volatile(
+                  "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::"r"(dst),
+                  "l"(srcA + gA[q * run_a]), "r"(run_a * (unsigned)sizeof(T)), "r"(bar)
+                  : "memory");
+            }
+            arrived = true;
+          }
+        }
+        if (arrived) {
+        } else if (exactA) {
 #pragma unroll
           for (int i = 0; i < NA; ++i) {
             const unsigned meta = metaA[i * NPROD + ptid];
@@ -545,8 +590,9 @@ gett_kernel(const int64_t* __restrict__ D, const T* __restrict__ A, const T* __r
             const unsigned dst = (unsigned)__cvta_generic_to_shared(dB);
             const char* src = reinterpret_cast<const char*>(B) +
                               ((unsigned long long)tBp * steps_k + step) * (unsigned long long)P::PAIR_BYTES;
-            asm volatile("mbarrier.expect_tx.relaxed.cta.shared::cta.b64 [%0], %1;\n" ::"r"(bar), "r"(P::PAIR_BYTES)
-                         : "memory");
+            if (!arrived)  // (bulk mode already announced these bytes with its arrival)
+              asm volatile("mbarrier.expect_tx.relaxed.cta.shared::cta.b64 [%0], %1;\n" ::"r"(bar), "r"(P::PAIR_BYTES)
+                           : "memory");
             asm volatile(
                 "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::"r"(dst),
                 "l"(src), "r"(P::PAIR_BYTES), "r"(bar)
@@ -569,7 +615,7 @@ gett_kernel(const int64_t* __restrict__ D, const T* __restrict__ A, const T* __r
             }
           }
         }
-        mbar_arrive_cp_async(&bar_full[st]);
+        if (!arrived) mbar_arrive_cp_async(&bar_full[st]);
       }
     }
     cp_async_commit();
@@ -578,7 +624,7 @@ gett_kernel(const int64_t* __restrict__ D, const T* __restrict__ A, const T* __r
     // ===================================================== CONSUMER WARPS
     if constexpr (P::IS_TC05) {
       tc05_consumer<T, P>(D, C, sA, sB, bar_full, bar_empty, bar_tile, tmem_slot, ti_base, ti_valid, offMC, offNC, nw,
-                          tiles_all, steps_k, steps_per_split, accumulate, atomic);
+                          tiles_all, steps_k, steps_per_split, accumulate, atomic, metaA, bulk_a, exactA);
       return;
     }
     if constexpr (P::CONSUMER_REGS > 0) reg_alloc<P::CONSUMER_REGS>();

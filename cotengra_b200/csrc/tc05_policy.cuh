@@ -15,7 +15,10 @@
 //     launch by bprime_kernel -- B is the small operand, <= a few MB -- and each
 //     stage's pair of tiles arrives with ONE TMA bulk copy (cp.async.bulk,
 //     mbarrier complete_tx);
-//   * A'lo is produced from the gathered A' stage by the consumer warps;
+//   * A'lo is produced from the gathered A' stage by the consumer warps; when the A tile
+//     is made of long contiguous runs the producers fetch the runs with TMA bulk copies
+//     into a staging area and the same pass scatters them into the UMMA layout (the
+//     8-byte LDGSTS gather costs one LSU wavefront per lane: 66 % LSU pipe under ncu);
 //   * one elected thread issues the 12 UMMAs of a stage (3 passes x 4 k-steps of
 //     M128 x N(2NT) x K8) and commits them to the stage's "empty" mbarrier;
 //   * the epilogue reads TMEM with tcgen05.ld (32 lanes x 8 columns = 4 complex
@@ -30,7 +33,7 @@ struct Tc05Policy {
   static constexpr int TILE_FLOATS = 8 * (2 * NT) * 4;       // one B' tile: [8 chunks][2NT rows][4 floats]
   static constexpr int PAIR_BYTES = 2 * TILE_FLOATS * 4;     // hi + lo
   static constexpr int A_GATHER = MT * KT, B_GATHER = 0;      // float2 elements fetched by the producers
-  static constexpr int A_ELEMS = 2 * MT * KT;                 // A'hi + A'lo   (float2 units)
+  static constexpr int A_ELEMS = 3 * MT * KT;                 // A'hi | A'lo | bulk-copy staging (float2 units)
   static constexpr int B_ELEMS = TILE_FLOATS;                 // hi + lo tiles (2*TILE_FLOATS floats)
   static constexpr int SCRATCH_ELEMS = 0;
   static constexpr int CONSUMER_REGS = 0, PRODUCER_REGS = 0;

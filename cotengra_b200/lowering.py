@@ -483,8 +483,22 @@ def build_pair_desc(dims: PairDims, dtype, accumulate=False, sm_count=148,
             and all(x[4] % g == 0 for x in gb)
         )
 
+    # tcgen05 variants: if the A tile is made of long contiguous runs (dense prefix of
+    # the load order), the producers fetch whole runs with TMA bulk copies (bit6)
+    run_a, bulk_a = 1, False
+    if variant in (VAR_TC05_128x64, VAR_TC05_128x32):
+        for r_ in lda:
+            if r_[1] != run_a:
+                break
+            run_a *= r_[0]
+        rest = [r_[1] for r_ in lda if r_[1] >= run_a] + [g[2] for g in gm] + [g[2] for g in gk] + [g[2] for g in gb]
+        # (cp.async.bulk: 16-byte aligned source, size a multiple of 16 bytes)
+        bulk_a = (run_a >= 32 and run_a % 2 == 0 and (MTa * KTa) % run_a == 0
+                  and all(x % 2 == 0 for x in rest))
+    W[34] = run_a  # W_RUNA
     W[W_FLAGS] = ((1 if accumulate else 0) | (2 if pair_ok else 0) | (4 if grid_pow2 else 0)
-                  | (8 if m_pow2 else 0) | (16 if _cols_ok(4) else 0) | (32 if _cols_ok(2) else 0))
+                  | (8 if m_pow2 else 0) | (16 if _cols_ok(4) else 0) | (32 if _cols_ok(2) else 0)
+                  | (64 if bulk_a else 0))
     W[W_VARIANT] = variant
     W[W_CELEMS] = int(c_dense_elems)
 
