@@ -127,6 +127,17 @@ __device__ __forceinline__ void tc05_consumer(const int64_t* __restrict__ D, T* 
 
   if (warp < 4) {
     // ------------------------------------------------------------ MMA group
+    // scatter map of the bulk-copy mode: the same for every stage, kept in registers
+    // (tables of launches with a blocked dim hold (r, kk) pairs instead of the index)
+    constexpr int NSCAT = (MT * P::KT) / GROUP;
+    unsigned ureg[NSCAT];
+    if (bulk_a) {
+#pragma unroll
+      for (int i = 0; i < NSCAT; ++i) {
+        const unsigned meta = metaA[tid + i * GROUP];
+        ureg[i] = exactA ? meta : (unsigned)P::idxA((int)(meta & 0xFFFFu), (int)(meta >> 16));
+      }
+    }
     unsigned g = 0;
     for (unsigned j = 0; j < nw; ++j) {
       const unsigned w = blockIdx.x + j * gridDim.x;
@@ -142,18 +153,15 @@ __device__ __forceinline__ void tc05_consumer(const int64_t* __restrict__ D, T* 
         float4* ah = reinterpret_cast<float4*>(sA + st * P::A_ELEMS);
         float4* al = ah + (MT * P::KT) / 2;
         if (bulk_a) {
-          // staging holds the tile in A-memory order; metaA[e] is the UMMA index of element e
+          // staging holds the tile in A-memory order; ureg[i] is the UMMA index of element tid + i*GROUP
           const float2* stg = reinterpret_cast<const float2*>(al + (MT * P::KT) / 2);
           float2* hi2 = reinterpret_cast<float2*>(ah);
           float2* lo2 = reinterpret_cast<float2*>(al);
-#pragma unroll 4
-          for (int e = tid; e < MT * P::KT; e += GROUP) {
-            const float2 v = stg[e];
-            // (tables of launches with a blocked dim hold (r, kk) pairs instead of the index)
-            const unsigned meta = metaA[e];
-            const unsigned u = exactA ? meta : (unsigned)P::idxA((int)(meta & 0xFFFFu), (int)(meta >> 16));
-            hi2[u] = v;
-            lo2[u] = make_float2(v.x - trunc_tf32(v.x), v.y - trunc_tf32(v.y));
+#pragma unroll
+          for (int i = 0; i < NSCAT; ++i) {
+            const float2 v = stg[tid + i * GROUP];
+            hi2[ureg[i]] = v;
+            lo2[ureg[i]] = make_float2(v.x - trunc_tf32(v.x), v.y - trunc_tf32(v.y));
           }
         } else {
 #pragma unroll
@@ -213,34 +221,45 @@ __device__ __forceinline__ void tc05_consumer(const int64_t* __restrict__ D, T* 
       const long long baseC = ti_base[slot * 4 + 2];
       const int m_valid = ti_valid[slot * 2 + 0], n_valid = ti_valid[slot * 2 + 1];
       T* crow = C + baseC + offMC[r];
-#pragma unroll 4
-      for (int col = 0; col < 2 * NT; col += 8) {  // fp32 column; complex column = col / 2
-        unsigned v[8];
+      // 32 fp32 columns (16 complex) per tcgen05.ld: one TMEM round trip per 128 bytes of a row
+#pragma unroll 1
+      for (int col = 0; col < 2 * NT; col += 32) {  // fp32 column; complex column = col / 2
+        unsigned v[32];
         const unsigned ta = taddr + buf * P::TMEM_COLS + ((unsigned)(quad * 32) << 16) + (unsigned)col;
-        asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];\n"
-                     : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
-                     : "r"(ta));
+        asm volatile(
+            "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,"
+            "%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];\n"
+            : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+              "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
+              "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
+              "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+            : "r"(ta));
         asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
-        const int c0 = col >> 1;
-        if (r < m_valid && c0 < n_valid) {
-          if (quad_ok) {
-            const unsigned long long q0 = ((unsigned long long)v[1] << 32) | v[0], q1 = ((unsigned long long)v[3] << 32) | v[2];
-            const unsigned long long q2 = ((unsigned long long)v[5] << 32) | v[4], q3 = ((unsigned long long)v[7] << 32) | v[6];
-            asm volatile("st.global.v4.b64 [%0], {%1,%2,%3,%4};\n" ::"l"(crow + offNC[c0]), "l"(q0), "l"(q1), "l"(q2),
-                         "l"(q3)
-                         : "memory");
-          } else {
+        if (r < m_valid) {
 #pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              if (c0 + e < n_valid) {
-                T* p = crow + offNC[c0 + e];
-                const T val = make_float2(__uint_as_float(v[2 * e]), __uint_as_float(v[2 * e + 1]));
-                if (atomic) {
-                  atomic_add_of(p, val);
-                } else if (accumulate) {
-                  *p = add_of(*p, val);
-                } else {
-                  *p = val;
+          for (int s4 = 0; s4 < 4; ++s4) {  // groups of 4 complex columns
+            const int c0 = (col >> 1) + s4 * 4;
+            const unsigned* w = v + s4 * 8;
+            if (c0 >= n_valid) continue;
+            if (quad_ok) {
+              const unsigned long long q0 = ((unsigned long long)w[1] << 32) | w[0], q1 = ((unsigned long long)w[3] << 32) | w[2];
+              const unsigned long long q2 = ((unsigned long long)w[5] << 32) | w[4], q3 = ((unsigned long long)w[7] << 32) | w[6];
+              asm volatile("st.global.v4.b64 [%0], {%1,%2,%3,%4};\n" ::"l"(crow + offNC[c0]), "l"(q0), "l"(q1), "l"(q2),
+                           "l"(q3)
+                           : "memory");
+            } else {
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                if (c0 + e < n_valid) {
+                  T* p = crow + offNC[c0 + e];
+                  const T val = make_float2(__uint_as_float(w[2 * e]), __uint_as_float(w[2 * e + 1]));
+                  if (atomic) {
+                    atomic_add_of(p, val);
+                  } else if (accumulate) {
+                    *p = add_of(*p, val);
+                  } else {
+                    *p = val;
+                  }
                 }
               }
             }

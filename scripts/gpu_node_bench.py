@@ -58,7 +58,7 @@ for nd in picked:
         return x
     a, b, c = buf(nd["a"]), buf(nd["b"]), buf(nd["c"])
     W = np.array(nd["words"], dtype=np.int64)
-    W[L.W_FLAGS] = 0
+    W[L.W_FLAGS] &= ~1  # standalone launch: no accumulate
     W[L.W_CELEMS] = c.numel()
     def launch():
         _lib.check(lib.ctgb_contract_pair(W.ctypes.data, a.data_ptr(), b.data_ptr(), c.data_ptr(), 0))
