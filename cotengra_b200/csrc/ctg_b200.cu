@@ -156,27 +156,75 @@ int launch_rowstream(const int64_t* h, const int64_t* d, const void* A, const vo
 }
 
 // complex64 on tcgen05: prepare B' (hi/lo, tile order) once, then the warp-specialised kernel
-template <int NT, int STAGES>
+template <int NT>
 int launch_tc05(const int64_t* h, const int64_t* d, const void* A, const void* B, void* C, cudaStream_t st) {
-  using P = Tc05Policy<NT, STAGES>;
+  using Cfg = Tc05Cfg<NT>;
   DevInfo& di = devinfo();
   if (!di.ok) return fail(CTGB_E_CUDA, "no CUDA device");
   auto exact = [&](int pg, int full, int text) { return h[pg] < 0 || (h[full] % h[text]) == 0; };
   if (h[W_DTYPE] != CTGB_C64 || h[W_MTA] != 128 || h[W_NTA] != NT || h[W_KTA] != 16 ||
-      !exact(W_PGM, W_MFULL, W_MTEXT) || !exact(W_PGN, W_NFULL, W_NTEXT) || !exact(W_PGK, W_KFULL, W_KTEXT))
+      !exact(W_PGM, W_MFULL, W_MTEXT) || !exact(W_PGN, W_NFULL, W_NTEXT) || !exact(W_PGK, W_KFULL, W_KTEXT) ||
+      h[W_STEPS_K] > KCHUNK || h[W_LBOPAD] < 0 || h[W_LBOPAD] > 4 ||
+      ((h[W_FLAGS] & 64) && (h[W_RUNA] < 16 || (128 * 16) % h[W_RUNA] != 0)))
     return fail(CTGB_E_VALUE, "descriptor does not fit the tcgen05 kernel");
+  const uint64_t work = (uint64_t)h[W_TILES_M] * (uint64_t)h[W_TILES_N] * (uint64_t)h[W_TILES_B] * (uint64_t)h[W_SPLITK];
+  if (work == 0) return CTGB_OK;
+  if (work >= (1ull << 31)) return fail(CTGB_E_VALUE, "too many tiles for one launch");
+  static thread_local int attr_dev = -1;
+  int dev;
+  cudaGetDevice(&dev);
+  if (attr_dev != dev) {
+    CUDA_TRY(cudaFuncSetAttribute(tc05_kernel<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  (int)di.smem_optin - 1024));
+    attr_dev = dev;
+  }
+  // ring depths: B' resident (one slot per k-step) when this CTA's B' tiles never change and
+  // still leave room for >= 3 A stages; otherwise a 3-slot B' ring.  A gets the rest.
+  const long long pool = (long long)di.smem_optin - 1024 /* static + slack */ - (long long)Cfg::fixed_bytes();
+  const long long steps_k = h[W_STEPS_K], tiles_n = h[W_TILES_N];
+  uint64_t grid = (uint64_t)di.sms;
+  int b_stat = 0;
+  long long nb = 3;
+  if (h[W_TILES_B] == 1 && h[W_SPLITK] == 1 && steps_k <= Cfg::NB_MAX && tiles_n <= (long long)di.sms &&
+      pool - steps_k * Cfg::PAIR_BYTES >= 3ll * Cfg::A_TILE * 8) {
+    b_stat = 1;
+    nb = steps_k;
+    grid = (grid / (uint64_t)tiles_n) * (uint64_t)tiles_n;  // t % tiles_n is the same for every work item of a CTA
+  }
+  long long sa = (pool - nb * Cfg::PAIR_BYTES) / ((long long)Cfg::A_TILE * 8);
+  if (sa > Cfg::SA_MAX) sa = Cfg::SA_MAX;
+  if (sa < 2) return fail(CTGB_E_CUDA, "tcgen05 kernel needs more shared memory than the device offers");
+  if (grid > work) {
+    grid = work;
+    if (b_stat && grid % (uint64_t)tiles_n != 0) b_stat = 0, nb = nb < 3 ? 3 : nb;  // tiny launch: plain ring
+  }
+  const size_t smem = Cfg::smem_bytes((int)sa, (int)nb);
+  if (smem + 1024 > di.smem_optin)
+    return fail(CTGB_E_CUDA, "tcgen05 kernel needs more shared memory than the device offers");
+
   const unsigned long long tiles = (unsigned long long)h[W_TILES_B] * h[W_TILES_N] * h[W_STEPS_K];
-  const size_t bytes = (size_t)tiles * P::PAIR_BYTES;
+  const size_t bytes = (size_t)tiles * Cfg::PAIR_BYTES;
   float* Bp = nullptr;
   CUDA_TRY(cudaMallocAsync((void**)&Bp, bytes, st));
-  const unsigned long long total = tiles * P::TILE_FLOATS;
+  const unsigned long long total = tiles * Cfg::TILE_FLOATS;
   unsigned long long blocks = (total + 255) / 256;
   if (blocks > (unsigned long long)di.sms * 8) blocks = (unsigned long long)di.sms * 8;
   bprime_kernel<NT><<<(unsigned)blocks, 256, 0, st>>>(d, (const float2*)B, Bp);
   g_launches.fetch_add(1, std::memory_order_relaxed);
-  int rc = launch_gett_policy<float2, P>(h, d, A, Bp, C, st);
+  if (h[W_SPLITK] > 1 && !(h[W_FLAGS] & 1)) {
+    if (h[W_CELEMS] <= 0) {
+      cudaFreeAsync(Bp, st);
+      return fail(CTGB_E_VALUE, "split-K into a strided C needs accumulate");
+    }
+    CUDA_TRY(cudaMemsetAsync(C, 0, (size_t)h[W_CELEMS] * sizeof(float2), st));
+  }
+  tc05_kernel<NT><<<(unsigned)grid, Cfg::THREADS, smem, st>>>(d, (const float2*)A, Bp, (float2*)C, (unsigned)sa,
+                                                               (unsigned)nb, b_stat);
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  cudaError_t e = cudaGetLastError();
   cudaFreeAsync(Bp, st);
-  return rc;
+  if (e != cudaSuccess) return fail(CTGB_E_CUDA, cudaGetErrorString(e));
+  return CTGB_OK;
 }
 
 template <typename T>
@@ -184,8 +232,8 @@ int launch_gett_typed(const int64_t* h, const int64_t* d, const void* A, const v
   const int variant = (int)h[W_VARIANT];
   if (variant == VAR_ROWSTREAM) return launch_rowstream<T>(h, d, A, B, C, st);
   if constexpr (std::is_same<T, float2>::value) {
-    if (variant == VAR_TC05_128x64) return launch_tc05<64, 2>(h, d, A, B, C, st);
-    if (variant == VAR_TC05_128x32) return launch_tc05<32, 3>(h, d, A, B, C, st);
+    if (variant == VAR_TC05_128x64) return launch_tc05<64>(h, d, A, B, C, st);
+    if (variant == VAR_TC05_128x32) return launch_tc05<32>(h, d, A, B, C, st);
   }
   switch (variant) {
     case VAR_SIMT_64x64: return launch_gett_policy<T, SimtPolicy<T, 64, 64, 8, 3>>(h, d, A, B, C, st);

@@ -41,6 +41,7 @@ enum : int {
   W_VARIANT = 32,      // kernel variant chosen by the host
   W_CELEMS = 33,       // elements of a dense C (memset before split-K atomics); 0: strided C
   W_RUNA = 34,         // tcgen05: elements of the contiguous runs the A tile is made of (flags bit6)
+  W_LBOPAD = 35,       // tcgen05: chunk-stride padding of the A' images, x16 bytes (bank spreading)
   W_HDR = 40,
   // arrays
   OFF_TM = W_HDR,                 // MAX_T x (ext, sA, sC)

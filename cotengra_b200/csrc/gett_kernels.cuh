@@ -441,6 +441,7 @@ struct DmmaPolicy {
 #include "rowstream.cuh"
 #include "tc05_policy.cuh"
 #include "gett_ws.cuh"
+#include "tc05_kernel.cuh"
 
 // ------------------------------------------------------------------ single operand
 // out[o] = sum_s X[off_o(o) + off_s(s)]  (diag via summed strides; contract.py:332-361)

@@ -1,0 +1,463 @@
+// tc05_kernel.cuh -- complex64 dense nodes on the 5th-generation tensor cores
+// (tcgen05.mma kind::tf32, accumulators in TMEM).  Included inside namespace ctgb,
+// after gett_ws.cuh (mbarrier helpers) and tc05_policy.cuh (bprime_kernel, descriptors).
+//
+// A complex tile product C[128 x NT] += A[128 x 16] * B[16 x NT] runs as the real
+// product C'[128 x 2NT] += A'[128 x 32] * B'[2NT x 32]^T (tc05_policy.cuh), three times
+// for the 3xTF32 split.  The CTA is specialised into four roles that only meet at
+// mbarriers:
+//
+//   warps  8-11  A producers   the A tile of a k-step is fetched in A's MEMORY order
+//                              into a staging ring (SA deep, 16 KB each): TMA bulk copies
+//                              of whole contiguous runs (cp.async.bulk + complete_tx) when
+//                              the tile is made of runs >= 128 B, an 8-byte cp.async
+//                              gather otherwise.  The ring only holds raw data, so it is
+//                              deep enough to cover HBM latency.
+//   warp   12    B' producer   one TMA bulk copy per k-step of the prepared B'hi|B'lo
+//                              pair (ring of NB slots fed from L2; when all the B' tiles a
+//                              CTA ever needs fit the ring they are loaded once and stay).
+//   warps  0-3   scatter/MMA   staging -> A'hi / A'lo in UMMA's K-major core-matrix
+//                              layout (double buffered), then ONE thread issues the 12
+//                              UMMAs of the step and commits them to the "operand free",
+//                              "B' stage free" and (last step) "accumulator full" barriers.
+//   warps  4-7   epilogue      TMEM -> registers -> C (32-byte row sectors) for tile j-1
+//                              while the MMAs of tile j run (two TMEM accumulators).
+//
+// The scatter map (element of the staging tile -> UMMA position) is the same for every
+// stage and lives in registers.  The chunk stride (LBO) of the A' images is padded by
+// D[W_LBOPAD] x 16 B, chosen by the host so that the 16 lanes of a half warp -- 16
+// consecutive elements of A's memory order -- hit 16 different 8-byte bank pairs.
+#pragma once
+
+template <int NT_>
+struct Tc05Cfg {
+  static constexpr int MT = 128, NT = NT_, KT = 16;
+  static constexpr int SA_MAX = 8, NB_MAX = 8;             // ring depths are chosen per launch
+  static constexpr int TILE_FLOATS = 8 * (2 * NT) * 4;     // one B' tile: [8 chunks][2NT rows][4 floats]
+  static constexpr int PAIR_BYTES = 2 * TILE_FLOATS * 4;   // hi + lo
+  static constexpr int A_TILE = MT * KT;                   // float2 elements of one staged A tile
+  static constexpr int LBO_BASE = MT * 16;                 // bytes between k chunks of A' (unpadded)
+  static constexpr int OP_BYTES = 8 * (LBO_BASE + 64);     // one A' image with the largest padding
+  static constexpr int TMEM_COLS = 2 * NT;                 // fp32 columns of one accumulator
+  static constexpr int TI = SA_MAX + 4;                    // tile-info ring (epilogue lags <= 2 tiles)
+  static constexpr int NBARS = 2 * SA_MAX + 2 * NB_MAX + 2 + 4;
+  static constexpr int THREADS = 13 * 32;
+  static_assert(TMEM_COLS == 64 || TMEM_COLS == 128, "two accumulators must fit 512 TMEM columns");
+  static constexpr size_t fixed_bytes() {  // everything but the two rings
+    return 4 * (size_t)OP_BYTES + 8 * (size_t)(MT + NT + KCHUNK + 4 * TI + NBARS) + 128;
+  }
+  static constexpr size_t smem_bytes(int sa, int nb) {
+    return fixed_bytes() + (size_t)sa * A_TILE * 8 + (size_t)nb * PAIR_BYTES;
+  }
+};
+
+// ring position + phase bit of an mbarrier ring
+struct RingPos {
+  unsigned idx = 0, ph = 0;
+  __device__ __forceinline__ void next(unsigned n) {
+    if (++idx == n) {
+      idx = 0;
+      ph ^= 1;
+    }
+  }
+};
+
+// SA: depth of the A staging ring.  NB: slots of the B' ring.  b_stat: the B' tiles of this
+// CTA never change (one batch, grid a multiple of tiles_n, steps_k <= NB): they are
+// loaded once into slot = k-step and stay resident.
+template <int NT>
+__global__ void __launch_bounds__(416, 1)
+tc05_kernel(const int64_t* __restrict__ D, const float2* __restrict__ A, const float* __restrict__ Bp,
+            float2* __restrict__ C, const unsigned SA, const unsigned NB, const int b_stat) {
+  using Cfg = Tc05Cfg<NT>;
+  constexpr int MT = Cfg::MT, TI = Cfg::TI, A_TILE = Cfg::A_TILE;
+  constexpr int GROUP = 128;  // threads of the scatter group / of the A producers
+  extern __shared__ __align__(128) unsigned char tc05_smem[];
+  unsigned char* smem_raw = tc05_smem;
+  float2* stg = reinterpret_cast<float2*>(smem_raw);                  // [SA][A_TILE], memory order
+  unsigned char* op = smem_raw + (size_t)SA * A_TILE * 8;             // [2 buffers][hi | lo][OP_BYTES]
+  unsigned char* sB = op + 4 * Cfg::OP_BYTES;                         // [NB][PAIR_BYTES]
+  long long* offMC = reinterpret_cast<long long*>(sB + (size_t)NB * Cfg::PAIR_BYTES);
+  long long* offNC = offMC + MT;
+  long long* kbA = offNC + NT;
+  long long* ti_base = kbA + KCHUNK;  // [TI][4]: A base, -, C base, -
+  unsigned long long* stg_full = reinterpret_cast<unsigned long long*>(ti_base + 4 * TI);
+  unsigned long long* stg_empty = stg_full + Cfg::SA_MAX;
+  unsigned long long* b_full = stg_empty + Cfg::SA_MAX;
+  unsigned long long* b_empty = b_full + Cfg::NB_MAX;
+  unsigned long long* op_empty = b_empty + Cfg::NB_MAX;  // [2] one tcgen05.commit
+  unsigned long long* tmem_full = op_empty + 2;  // [2] one tcgen05.commit
+  unsigned long long* tmem_empty = tmem_full + 2;  // [2] four epilogue warps
+  __shared__ unsigned tmem_slot;
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+
+  // ---- header ----
+  const int n_tm = (int)D[W_NTM], n_tn = (int)D[W_NTN];
+  const int n_gm = (int)D[W_NGM], n_gn = (int)D[W_NGN], n_gk = (int)D[W_NGK], n_gb = (int)D[W_NGB];
+  const int n_lda = (int)D[W_NLDA];
+  const unsigned tiles_m = (unsigned)D[W_TILES_M], tiles_n = (unsigned)D[W_TILES_N], tiles_b = (unsigned)D[W_TILES_B];
+  const unsigned steps_k = (unsigned)D[W_STEPS_K], splitk = (unsigned)D[W_SPLITK];
+  const bool accumulate = (D[W_FLAGS] & 1) != 0;
+  const bool atomic = splitk > 1;
+  const bool g_pow2 = (D[W_FLAGS] & 4) != 0;
+  const unsigned run_a = (unsigned)D[W_RUNA];
+  // flags bit6: the A tile is made of contiguous runs of run_a elements (>= 128 B, even offsets)
+  const bool bulk_a = (D[W_FLAGS] & 64) != 0 && (reinterpret_cast<unsigned long long>(A) & 15ull) == 0;
+  const unsigned lbo_a = (unsigned)Cfg::LBO_BASE + 16u * (unsigned)D[W_LBOPAD];
+  auto digit_of = [&](unsigned idx, unsigned div, unsigned ext) -> unsigned {
+    return g_pow2 ? ((idx >> (31 - __clz(div))) & (ext - 1)) : ((idx / div) % ext);
+  };
+  // element e of the tile in A's memory order: global offset / position in the A' image (float2 units)
+  auto a_off = [&](unsigned e) -> long long {
+    long long g = 0;
+    for (int d = 0; d < n_lda; ++d) {
+      const int64_t* L = D + OFF_LDA + d * 4;
+      const unsigned ext = (unsigned)L[0];
+      g += (long long)(e % ext) * L[1];
+      e /= ext;
+    }
+    return g;
+  };
+  auto a_pos = [&](unsigned e) -> unsigned {
+    unsigned r = 0, kk = 0;
+    for (int d = 0; d < n_lda; ++d) {
+      const int64_t* L = D + OFF_LDA + d * 4;
+      const unsigned ext = (unsigned)L[0], dig = e % ext;
+      e /= ext;
+      r += dig * (unsigned)L[2];
+      kk += dig * (unsigned)L[3];
+    }
+    return (kk >> 1) * (lbo_a >> 3) + r * 2 + (kk & 1);
+  };
+
+  // ---- one-time tables ----
+  if (tid == 0) {
+    for (unsigned s = 0; s < SA; ++s) {
+      mbar_init(&stg_full[s], GROUP);
+      mbar_init(&stg_empty[s], 4);
+    }
+    for (unsigned s = 0; s < NB; ++s) {
+      mbar_init(&b_full[s], 1);
+      mbar_init(&b_empty[s], 1);
+    }
+    mbar_init(&op_empty[0], 1);
+    mbar_init(&op_empty[1], 1);
+    mbar_init(&tmem_full[0], 1);
+    mbar_init(&tmem_full[1], 1);
+    mbar_init(&tmem_empty[0], 4);
+    mbar_init(&tmem_empty[1], 4);
+    asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+  }
+  if (tid < 256) {
+    for (int r = tid; r < MT; r += 256) {
+      long long o = 0;
+      unsigned e = r;
+      for (int d = 0; d < n_tm; ++d) {
+        const int64_t* L = D + OFF_TM + d * 3;
+        const unsigned ext = (unsigned)L[0];
+        o += (long long)(e % ext) * L[2];
+        e /= ext;
+      }
+      offMC[r] = o;
+    }
+    for (int c = tid; c < NT; c += 256) {
+      long long o = 0;
+      unsigned e = c;
+      for (int d = 0; d < n_tn; ++d) {
+        const int64_t* L = D + OFF_TN + d * 3;
+        const unsigned ext = (unsigned)L[0];
+        o += (long long)(e % ext) * L[2];
+        e /= ext;
+      }
+      offNC[c] = o;
+    }
+  } else if (tid < 384) {
+    // A base offset of every k-step (the host guarantees steps_k <= KCHUNK)
+    for (unsigned s = tid - 256; s < steps_k; s += GROUP) {
+      long long a = 0;
+      for (int j = 0; j < n_gk; ++j) {
+        const int64_t* G = D + OFF_GK + j * 4;
+        a += (long long)((s / (unsigned)G[1]) % (unsigned)G[0]) * G[2];
+      }
+      kbA[s] = a;
+    }
+  }
+  if (warp == 0) {
+    const unsigned a = (unsigned)__cvta_generic_to_shared(&tmem_slot);
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"(a), "r"(2 * Cfg::TMEM_COLS)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+  const unsigned taddr = tmem_slot;
+
+  // the host guarantees total_work < 2^31
+  const unsigned tiles_all = tiles_m * tiles_n * tiles_b;
+  const unsigned total_work = tiles_all * splitk;
+  const unsigned steps_per_split = (steps_k + splitk - 1) / splitk;
+  const unsigned nw = blockIdx.x < total_work ? (total_work - blockIdx.x + gridDim.x - 1) / gridDim.x : 0u;
+  auto work_krange = [&](unsigned j, unsigned& k0, unsigned& k1) {
+    const unsigned ks = (blockIdx.x + j * gridDim.x) / tiles_all;
+    k0 = ks * steps_per_split;
+    k1 = min(steps_k, k0 + steps_per_split);
+  };
+  // tile coordinates of work item j (n fastest: neighbouring CTAs share A tiles in L2)
+  auto work_tile = [&](unsigned j, unsigned& in_, unsigned& im_, unsigned& ib_) {
+    unsigned t = blockIdx.x + j * gridDim.x;
+    if (splitk > 1) t %= tiles_all;
+    if (g_pow2) {
+      in_ = t & (tiles_n - 1);
+      t >>= 31 - __clz(tiles_n);
+      im_ = t & (tiles_m - 1);
+      ib_ = t >> (31 - __clz(tiles_m));
+    } else {
+      in_ = t % tiles_n;
+      t /= tiles_n;
+      im_ = t % tiles_m;
+      ib_ = t / tiles_m;
+    }
+  };
+
+  if (warp >= 8 && warp < 12) {
+    // ===================================================== A PRODUCERS
+    const int ptid = tid - 256;
+    const unsigned nruns = bulk_a ? (unsigned)A_TILE / run_a : 0u;  // <= 128: run_a >= 16
+    constexpr int NG = A_TILE / GROUP;
+    long long goff[NG];  // gather mode: element ptid + i*GROUP; bulk mode: goff[0] = start of run ptid
+#pragma unroll
+    for (int i = 0; i < NG; ++i) goff[i] = bulk_a ? 0ll : a_off((unsigned)(ptid + i * GROUP));
+    if (bulk_a && (unsigned)ptid < nruns) goff[0] = a_off((unsigned)ptid * run_a);
+    RingPos ra;
+    for (unsigned j = 0; j < nw; ++j) {
+      unsigned k0, k1;
+      work_krange(j, k0, k1);
+      const int slot = (int)(j % TI);
+      if (ptid < 32) {
+        unsigned in_, im_, ib_;
+        work_tile(j, in_, im_, ib_);
+        long long a = 0, c = 0;
+        for (int q = lane; q < n_gm; q += 32) {
+          const int64_t* G = D + OFF_GM + q * 4;
+          const unsigned dig = digit_of(im_, (unsigned)G[1], (unsigned)G[0]);
+          a += (long long)dig * G[2];
+          c += (long long)dig * G[3];
+        }
+        for (int q = lane; q < n_gn; q += 32) {
+          const int64_t* G = D + OFF_GN + q * 4;
+          c += (long long)digit_of(in_, (unsigned)G[1], (unsigned)G[0]) * G[3];
+        }
+        for (int q = lane; q < n_gb; q += 32) {
+          const int64_t* G = D + OFF_GB + q * 5;
+          const unsigned dig = digit_of(ib_, (unsigned)G[1], (unsigned)G[0]);
+          a += (long long)dig * G[2];
+          c += (long long)dig * G[4];
+        }
+        a = warp_sum_ll(a);
+        c = warp_sum_ll(c);
+        if (lane == 0) {
+          ti_base[slot * 4 + 0] = a;
+          ti_base[slot * 4 + 2] = c;
+          __threadfence_block();
+        }
+      }
+      named_sync<1, GROUP>();
+      const long long tA = ti_base[slot * 4 + 0];
+      for (unsigned step = k0; step < k1; ++step, ra.next(SA)) {
+        const unsigned sa = ra.idx;
+        mbar_wait(&stg_empty[sa], ra.ph ^ 1);
+        const float2* src = A + tA + kbA[step];
+        float2* dst = stg + (size_t)sa * A_TILE;
+        const unsigned bar = (unsigned)__cvta_generic_to_shared(&stg_full[sa]);
+        if (bulk_a) {
+          const bool mine = (unsigned)ptid < nruns;
+          const unsigned bytes = mine ? run_a * 8u : 0u;
+          asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.expect_tx.shared::cta.b64 st, [%0], %1;\n\t}\n" ::"r"(bar),
+                       "r"(bytes)
+                       : "memory");
+          if (mine) {
+            const unsigned d = (unsigned)__cvta_generic_to_shared(dst + (size_t)ptid * run_a);
+            asm volatile(
+                "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::"r"(d),
+                "l"(src + goff[0]), "r"(bytes), "r"(bar)
+                : "memory");
+          }
+        } else {
+#pragma unroll
+          for (int i = 0; i < NG; ++i) cp_async_zfill<8>(dst + ptid + i * GROUP, src + goff[i], true);
+          mbar_arrive_cp_async(&stg_full[sa]);
+        }
+      }
+    }
+    cp_async_commit();
+    cp_async_wait<0>();  // do not exit with copies in flight
+  } else if (warp == 12) {
+    // ===================================================== B' PRODUCER
+    if (lane == 0) {
+      RingPos rb;
+      const unsigned nwb = b_stat ? min(nw, 1u) : nw;  // resident B': loaded with the first work item only
+      for (unsigned j = 0; j < nwb; ++j) {
+        unsigned k0, k1, in_, im_, ib_;
+        work_krange(j, k0, k1);
+        work_tile(j, in_, im_, ib_);
+        const unsigned long long tile = (unsigned long long)ib_ * tiles_n + in_;
+        for (unsigned step = k0; step < k1; ++step, rb.next(NB)) {
+          const unsigned sb = rb.idx;
+          mbar_wait(&b_empty[sb], rb.ph ^ 1);
+          const unsigned bar = (unsigned)__cvta_generic_to_shared(&b_full[sb]);
+          const unsigned dst = (unsigned)__cvta_generic_to_shared(sB + (size_t)sb * Cfg::PAIR_BYTES);
+          const char* src = reinterpret_cast<const char*>(Bp) + (tile * steps_k + step) * (unsigned long long)Cfg::PAIR_BYTES;
+          asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.expect_tx.shared::cta.b64 st, [%0], %1;\n\t}\n" ::"r"(bar),
+                       "r"(Cfg::PAIR_BYTES)
+                       : "memory");
+          asm volatile(
+              "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::"r"(dst),
+              "l"(src), "r"(Cfg::PAIR_BYTES), "r"(bar)
+              : "memory");
+        }
+      }
+    }
+  } else if (warp < 4) {
+    // ===================================================== SCATTER / MMA GROUP
+    // InstrDescriptor: D=f32 [4,6)=1, A=tf32 [7,10)=2, B=tf32 [10,13)=2, K-major A/B, N>>3 [17,23), M>>4 [24,29)
+    constexpr unsigned idesc =
+        (1u << 4) | (2u << 7) | (2u << 10) | ((unsigned)(Cfg::TMEM_COLS >> 3) << 17) | ((unsigned)(MT >> 4) << 24);
+    constexpr int NSCAT = A_TILE / GROUP;
+    unsigned upos[NSCAT];
+#pragma unroll
+    for (int i = 0; i < NSCAT; ++i) upos[i] = a_pos((unsigned)(tid + i * GROUP));
+    unsigned g = 0;
+    RingPos ra, rb;
+    for (unsigned j = 0; j < nw; ++j) {
+      unsigned k0, k1;
+      work_krange(j, k0, k1);
+      const unsigned buf = j & 1;
+      mbar_wait(&tmem_empty[buf], ((j >> 1) & 1) ^ 1);  // epilogue of tile j-2 has drained this accumulator
+      asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+      for (unsigned step = k0; step < k1; ++step, ++g, ra.next(SA), rb.next(NB)) {
+        const unsigned sa = ra.idx, sb = b_stat ? step : rb.idx, ob = g & 1;
+        float2* hi2 = reinterpret_cast<float2*>(op + (size_t)(ob * 2) * Cfg::OP_BYTES);
+        float2* lo2 = reinterpret_cast<float2*>(op + (size_t)(ob * 2 + 1) * Cfg::OP_BYTES);
+        const float2* src = stg + (size_t)sa * A_TILE;
+        mbar_wait(&op_empty[ob], ((g >> 1) & 1) ^ 1);  // the UMMAs of step g-2 have read these images
+        mbar_wait(&stg_full[sa], ra.ph);
+#pragma unroll
+        for (int i = 0; i < NSCAT; ++i) {
+          const float2 v = src[tid + i * GROUP];
+          hi2[upos[i]] = v;  // the tensor core truncates its operands to tf32 itself
+          lo2[upos[i]] = make_float2(v.x - trunc_tf32(v.x), v.y - trunc_tf32(v.y));
+        }
+        asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");  // generic-proxy writes -> tensor core
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&stg_empty[sa]);  // this warp's reads of the staging tile are done
+        asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
+        named_sync<3, GROUP>();
+        asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+        if (tid == 0) {
+          if (!b_stat) {
+            mbar_wait(&b_full[sb], rb.ph);
+          } else if (j == 0) {
+            mbar_wait(&b_full[sb], 0);  // resident B': filled once
+          }
+          const unsigned a_hi = (unsigned)__cvta_generic_to_shared(hi2);
+          const unsigned a_lo = (unsigned)__cvta_generic_to_shared(lo2);
+          const unsigned b_hi = (unsigned)__cvta_generic_to_shared(sB + (size_t)sb * Cfg::PAIR_BYTES);
+          const unsigned b_lo = b_hi + Cfg::TILE_FLOATS * 4;
+          const unsigned dcol = taddr + buf * Cfg::TMEM_COLS;
+#pragma unroll
+          for (int pass = 0; pass < 3; ++pass) {
+            const unsigned a0 = pass == 0 ? a_lo : a_hi, b0 = pass == 1 ? b_lo : b_hi;  // lo*hi, hi*lo, hi*hi
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              // one UMMA eats K = 8 floats = 2 chunks; chunk stride = LBO, 8-row group stride (SBO) = 128 B
+              const uint64_t da = umma_desc_kmajor(a0 + q * 2 * lbo_a, lbo_a, 128);
+              const uint64_t db = umma_desc_kmajor(b0 + q * 2 * (2 * NT) * 16, (2 * NT) * 16, 128);
+              const unsigned acc = (step != k0 || pass != 0 || q != 0) ? 1u : 0u;
+              asm volatile(
+                  "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                  "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(dcol),
+                  "l"(da), "l"(db), "r"(idesc), "r"(acc)
+                  : "memory");
+            }
+          }
+          const unsigned m_op = (unsigned)__cvta_generic_to_shared(&op_empty[ob]);
+          const unsigned m_b = (unsigned)__cvta_generic_to_shared(&b_empty[sb]);
+          asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n" ::"r"(m_op)
+                       : "memory");
+          if (!b_stat)
+            asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n" ::"r"(m_b)
+                         : "memory");
+          if (step + 1 == k1) {
+            const unsigned mf = (unsigned)__cvta_generic_to_shared(&tmem_full[buf]);
+            asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n" ::"r"(mf)
+                         : "memory");
+          }
+        }
+      }
+    }
+  } else {
+    // ===================================================== EPILOGUE GROUP (warps 4-7)
+    const bool quad_ok = (D[W_FLAGS] & 16) != 0 && !accumulate && !atomic &&
+                         (reinterpret_cast<unsigned long long>(C) & 31ull) == 0;
+    const int quad = warp & 3;  // TMEM lane quadrant of this warp
+    const int r = quad * 32 + lane;
+    const long long row_off = offMC[r];
+    for (unsigned j = 0; j < nw; ++j) {
+      const unsigned buf = j & 1;
+      mbar_wait(&tmem_full[buf], (j >> 1) & 1);
+      asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+      float2* crow = C + ti_base[(j % TI) * 4 + 2] + row_off;
+      // 32 fp32 columns (16 complex) per tcgen05.ld: one TMEM round trip per 128 bytes of a row
+#pragma unroll 1
+      for (int col = 0; col < 2 * NT; col += 32) {
+        unsigned v[32];
+        const unsigned ta = taddr + buf * Cfg::TMEM_COLS + ((unsigned)(quad * 32) << 16) + (unsigned)col;
+        asm volatile(
+            "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,"
+            "%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];\n"
+            : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+              "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
+              "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
+              "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+            : "r"(ta));
+        asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
+#pragma unroll
+        for (int s4 = 0; s4 < 4; ++s4) {  // groups of 4 complex columns
+          const int c0 = (col >> 1) + s4 * 4;
+          const unsigned* w = v + s4 * 8;
+          if (quad_ok) {
+            const unsigned long long q0 = ((unsigned long long)w[1] << 32) | w[0], q1 = ((unsigned long long)w[3] << 32) | w[2];
+            const unsigned long long q2 = ((unsigned long long)w[5] << 32) | w[4], q3 = ((unsigned long long)w[7] << 32) | w[6];
+            asm volatile("st.global.v4.b64 [%0], {%1,%2,%3,%4};\n" ::"l"(crow + offNC[c0]), "l"(q0), "l"(q1), "l"(q2),
+                         "l"(q3)
+                         : "memory");
+          } else {
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              float2* p = crow + offNC[c0 + e];
+              const float2 val = make_float2(__uint_as_float(w[2 * e]), __uint_as_float(w[2 * e + 1]));
+              if (atomic) {
+                atomic_add_of(p, val);
+              } else if (accumulate) {
+                *p = add_of(*p, val);
+              } else {
+                *p = val;
+              }
+            }
+          }
+        }
+      }
+      asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tmem_empty[buf]);
+    }
+  }
+  if (warp < 8) {
+    named_sync<2, 256>();
+    if (warp == 0)
+      asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(taddr), "r"(2 * Cfg::TMEM_COLS)
+                   : "memory");
+  }
+}

@@ -373,9 +373,16 @@ def build_pair_desc(dims: PairDims, dtype, accumulate=False, sm_count=148,
             variant = VAR_ROW_256x4 if N <= 4 else VAR_ROW_128x8
     MT, NT, KT = VARIANT_TILES[variant]
 
-    tm, gm, pm = split_tile(m, (1, 2), MT, order_col=2)
+    if variant in (VAR_TC05_128x64, VAR_TC05_128x32):
+        # tcgen05: every thread of the epilogue owns a whole row, so the rows of a tile need
+        # not be neighbours in C -- pick them for the longest contiguous runs of A instead
+        # (and B is re-packed by bprime_kernel anyway: only A's strides matter for k too)
+        tm, gm, pm = split_tile(m, (1,), MT, order_col=1)
+        tk, gk, pk = split_tile(k, (1,), KT, order_col=1)
+    else:
+        tm, gm, pm = split_tile(m, (1, 2), MT, order_col=2)
+        tk, gk, pk = split_tile(k, (1, 2), KT, order_col=1)
     tn, gn, pn = split_tile(n, (1, 2), NT, order_col=2)
-    tk, gk, pk = split_tile(k, (1, 2), KT, order_col=1)
     gm, pm = _order_grid(gm, pm, 1)
     gn, pn = _order_grid(gn, pn, 1)
     gk, pk = _order_grid(gk, pk, 1)
@@ -476,8 +483,18 @@ def build_pair_desc(dims: PairDims, dtype, accumulate=False, sm_count=148,
     # 8-byte element types: groups of 4 (bit4) / 2 (bit5) columns adjacent in C and
     # 32- / 16-byte aligned -> vector row stores in the streaming row kernel
     def _cols_ok(g):
+        if variant in (VAR_TC05_128x64, VAR_TC05_128x32):
+            # exact tiles: only the leading columns of a tile row have to be adjacent
+            run = 1
+            for d in tn:
+                if d[2] != run:
+                    break
+                run *= d[0]
+            dense = run % g == 0
+        else:
+            dense = dense_n and pn is None
         return (
-            DTYPE_SIZES[dtype] == 8 and dense_n and pn is None and NTa % g == 0
+            DTYPE_SIZES[dtype] == 8 and dense and NTa % g == 0
             and all(d[2] % g == 0 for d in tm)
             and all(x[3] % g == 0 for x in gm) and all(x[3] % g == 0 for x in gn)
             and all(x[4] % g == 0 for x in gb)
@@ -492,9 +509,29 @@ def build_pair_desc(dims: PairDims, dtype, accumulate=False, sm_count=148,
                 break
             run_a *= r_[0]
         rest = [r_[1] for r_ in lda if r_[1] >= run_a] + [g[2] for g in gm] + [g[2] for g in gk] + [g[2] for g in gb]
-        # (cp.async.bulk: 16-byte aligned source, size a multiple of 16 bytes)
-        bulk_a = (run_a >= 32 and run_a % 2 == 0 and (MTa * KTa) % run_a == 0
+        # (cp.async.bulk: 16-byte aligned source, size a multiple of 16 bytes; one run per
+        # producer thread -> at most 128 runs of >= 128 bytes)
+        bulk_a = (run_a >= 16 and run_a % 2 == 0 and (MTa * KTa) % run_a == 0
                   and all(x % 2 == 0 for x in rest))
+        # chunk-stride padding of the A' images (x16 B): 16 consecutive elements of A's memory
+        # order -- the lanes of a half warp in the scatter pass -- should hit 16 different
+        # 8-byte bank pairs.  Element (r, kk) sits at (kk//2)*LBO + r*16 + (kk%2)*8 bytes.
+        def _conflicts(pad):
+            lbo, worst = MT * 16 + 16 * pad, 0
+            for half in range(2):
+                slots = {}
+                for e in range(16 * half, 16 * half + 16):
+                    r_ = kk_ = 0
+                    x = e
+                    for ext, _s, wr, wk_ in lda:
+                        r_ += (x % ext) * wr
+                        kk_ += (x % ext) * wk_
+                        x //= ext
+                    slot = (((kk_ // 2) * lbo + r_ * 16 + (kk_ % 2) * 8) >> 3) & 15
+                    slots[slot] = slots.get(slot, 0) + 1
+                worst += max(slots.values())
+            return worst
+        W[35] = min((0, 1, 2, 4), key=_conflicts)  # W_LBOPAD
     W[34] = run_a  # W_RUNA
     W[W_FLAGS] = ((1 if accumulate else 0) | (2 if pair_ok else 0) | (4 if grid_pow2 else 0)
                   | (8 if m_pow2 else 0) | (16 if _cols_ok(4) else 0) | (32 if _cols_ok(2) else 0)
