@@ -123,8 +123,6 @@ struct SimtPolicy {
   static constexpr int SCRATCH_ELEMS = 0;
   static constexpr int CONSUMER_REGS = 0, PRODUCER_REGS = 0;
   static constexpr bool HAS_BCACHE = false;
-  static constexpr bool IS_TC05 = false;
-  static constexpr int A_GATHER = A_ELEMS, B_GATHER = B_ELEMS;
   static constexpr int MIN_BLOCKS = sizeof(T) == 16 ? 1 : 2;
   struct Acc {
     T v[TM][TN];
@@ -175,8 +173,6 @@ struct KredPolicy {
   static constexpr int SCRATCH_ELEMS = MT * NT * (THREADS / 32);
   static constexpr int CONSUMER_REGS = 0, PRODUCER_REGS = 0;
   static constexpr bool HAS_BCACHE = false;
-  static constexpr bool IS_TC05 = false;
-  static constexpr int A_GATHER = A_ELEMS, B_GATHER = B_ELEMS;
   static constexpr int MIN_BLOCKS = 2;
   struct Acc {
     T v[MT][NT];
@@ -245,8 +241,6 @@ struct RowPolicy {
   static constexpr int CONSUMER_REGS = 0, PRODUCER_REGS = 0;
   static constexpr int MIN_BLOCKS = 2;
   static constexpr bool HAS_BCACHE = sizeof(T) * KT * NT <= 256;
-  static constexpr bool IS_TC05 = false;
-  static constexpr int A_GATHER = A_ELEMS, B_GATHER = B_ELEMS;
   struct BCache {
     T v[KT][NT];
   };
@@ -341,8 +335,6 @@ struct DmmaPolicy {
   // 8 consumer warps x 232 + 4 producer warps x 40 registers = 64512 <= 65536
   static constexpr int CONSUMER_REGS = (THREADS == 256) ? 232 : 0, PRODUCER_REGS = 40;
   static constexpr bool HAS_BCACHE = false;
-  static constexpr bool IS_TC05 = false;
-  static constexpr int A_GATHER = A_ELEMS, B_GATHER = B_ELEMS;
   static constexpr int MIN_BLOCKS = 1;
   static_assert(KT % 4 == 0, "KT must be a multiple of the DMMA k");
   struct Acc {

@@ -68,16 +68,14 @@ struct BCacheOf<P, true> {
 
 template <class P>
 struct GettSmem {
-  // slots of the per-element gather tables (elements the producers fetch one by one)
-  static constexpr int NA = (P::A_GATHER + PRODUCER_THREADS - 1) / PRODUCER_THREADS;
-  static constexpr int NB = (P::B_GATHER + PRODUCER_THREADS - 1) / PRODUCER_THREADS;
+  static constexpr int NA = (P::A_ELEMS + PRODUCER_THREADS - 1) / PRODUCER_THREADS;
+  static constexpr int NB = (P::B_ELEMS + PRODUCER_THREADS - 1) / PRODUCER_THREADS;
   // tile-info ring.  STAGES + 2 slots: the producer decodes tile j+TI right after
   // issuing tile j+TI-1, whose first stage needed the "empty" arrival of every
   // consumer warp for tile j+1 -- i.e. all of them are past the epilogue of tile
   // j, the last reader of slot j % TI.  (STAGES + 1 is one too few: the decode
   // runs BEFORE the producer waits on the stage it will fill.)
-  // (the tcgen05 policy's epilogue group may lag one more tile behind: two TMEM accumulators)
-  static constexpr int TI = P::STAGES + (P::IS_TC05 ? 4 : 2);
+  static constexpr int TI = P::STAGES + 2;
   template <typename T>
   static constexpr size_t bytes() {
     return sizeof(T) * ((size_t)P::STAGES * (P::A_ELEMS + P::B_ELEMS) + P::SCRATCH_ELEMS)  // ring + scratch
@@ -91,191 +89,6 @@ struct GettSmem {
            + 64;
   }
 };
-
-// Consumer side of the tcgen05 policy, itself specialised:
-//   warps 0-3  "MMA group": build A'lo for the stage, issue the 12 UMMAs (one elected
-//              thread), commit them to the stage's "empty" barrier;
-//   warps 4-7  "epilogue group": TMEM -> registers -> C for the previous tile while the
-//              MMA group already works on the next one (two TMEM accumulators).
-template <typename T, class P>
-__device__ __forceinline__ void tc05_consumer(const int64_t* __restrict__ D, T* __restrict__ C, T* sA, T* sB,
-                                              unsigned long long* bar_full, unsigned long long* bar_empty,
-                                              unsigned long long* bar_tmem, unsigned* tmem_slot, const long long* ti_base,
-                                              const int* ti_valid, const long long* offMC, const long long* offNC,
-                                              unsigned nw, unsigned tiles_all, unsigned steps_k, unsigned steps_per_split,
-                                              bool accumulate, bool atomic, const unsigned* metaA, bool bulk_a,
-                                              bool exactA) {
-  constexpr int MT = P::MT, NT = P::NT, STAGES = P::STAGES, NCONS = P::THREADS;
-  constexpr int TI = GettSmem<P>::TI;
-  constexpr int GROUP = 128;
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  unsigned long long* tmem_full = bar_tmem;       // [2] count 1 (tcgen05.commit)
-  unsigned long long* tmem_empty = bar_tmem + 2;  // [2] count 4 (epilogue warps)
-  if (warp == 0) {
-    const unsigned a = (unsigned)__cvta_generic_to_shared(tmem_slot);
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"(a), "r"(2 * P::TMEM_COLS)
-                 : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n" ::: "memory");
-  }
-  asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
-  named_sync<2, NCONS>();
-  asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
-  const unsigned taddr = *tmem_slot;
-  // InstrDescriptor: D=f32 [4,6)=1, A=tf32 [7,10)=2, B=tf32 [10,13)=2, K-major A/B, N>>3 [17,23), M>>4 [24,29)
-  constexpr unsigned idesc =
-      (1u << 4) | (2u << 7) | (2u << 10) | ((unsigned)(P::TMEM_COLS >> 3) << 17) | ((unsigned)(MT >> 4) << 24);
-
-  if (warp < 4) {
-    // ------------------------------------------------------------ MMA group
-    // scatter map of the bulk-copy mode: the same for every stage, kept in registers
-    // (tables of launches with a blocked dim hold (r, kk) pairs instead of the index)
-    constexpr int NSCAT = (MT * P::KT) / GROUP;
-    unsigned ureg[NSCAT];
-    if (bulk_a) {
-#pragma unroll
-      for (int i = 0; i < NSCAT; ++i) {
-        const unsigned meta = metaA[tid + i * GROUP];
-        ureg[i] = exactA ? meta : (unsigned)P::idxA((int)(meta & 0xFFFFu), (int)(meta >> 16));
-      }
-    }
-    unsigned g = 0;
-    for (unsigned j = 0; j < nw; ++j) {
-      const unsigned w = blockIdx.x + j * gridDim.x;
-      const unsigned ks = w / tiles_all;
-      const unsigned k0 = ks * steps_per_split, k1 = min(steps_k, k0 + steps_per_split);
-      const unsigned buf = j & 1;
-      mbar_wait(&tmem_empty[buf], ((j >> 1) & 1) ^ 1);  // epilogue of tile j-2 has drained this accumulator
-      asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
-      for (unsigned step = k0; step < k1; ++step, ++g) {
-        const int st = (int)(g % STAGES);
-        mbar_wait(&bar_full[st], (g / STAGES) & 1);
-        // A'lo = A' - trunc_tf32(A') for the whole stage (same tile order)
-        float4* ah = reinterpret_cast<float4*>(sA + st * P::A_ELEMS);
-        float4* al = ah + (MT * P::KT) / 2;
-        if (bulk_a) {
-          // staging holds the tile in A-memory order; ureg[i] is the UMMA index of element tid + i*GROUP
-          const float2* stg = reinterpret_cast<const float2*>(al + (MT * P::KT) / 2);
-          float2* hi2 = reinterpret_cast<float2*>(ah);
-          float2* lo2 = reinterpret_cast<float2*>(al);
-#pragma unroll
-          for (int i = 0; i < NSCAT; ++i) {
-            const float2 v = stg[tid + i * GROUP];
-            hi2[ureg[i]] = v;
-            lo2[ureg[i]] = make_float2(v.x - trunc_tf32(v.x), v.y - trunc_tf32(v.y));
-          }
-        } else {
-#pragma unroll
-          for (int i = tid; i < (MT * P::KT) / 2; i += GROUP) {
-            const float4 v = ah[i];
-            al[i] = make_float4(v.x - trunc_tf32(v.x), v.y - trunc_tf32(v.y), v.z - trunc_tf32(v.z), v.w - trunc_tf32(v.w));
-          }
-        }
-        asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");  // generic-proxy writes -> tensor core
-        asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
-        named_sync<3, GROUP>();
-        asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
-        if (tid == 0) {
-          const unsigned a_hi = (unsigned)__cvta_generic_to_shared(ah);
-          const unsigned a_lo = (unsigned)__cvta_generic_to_shared(al);
-          const unsigned b_hi = (unsigned)__cvta_generic_to_shared(sB + st * P::B_ELEMS);
-          const unsigned b_lo = b_hi + P::TILE_FLOATS * 4;
-          const unsigned dcol = taddr + buf * P::TMEM_COLS;
-#pragma unroll
-          for (int pass = 0; pass < 3; ++pass) {
-            const unsigned a0 = pass == 0 ? a_lo : a_hi, b0 = pass == 1 ? b_lo : b_hi;  // lo*hi, hi*lo, hi*hi
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {
-              // one UMMA eats K = 8 floats = 2 chunks; chunk stride (LBO) = rows*16 B, 8-row group stride (SBO) = 128 B
-              const uint64_t da = umma_desc_kmajor(a0 + q * 2 * MT * 16, MT * 16, 128);
-              const uint64_t db = umma_desc_kmajor(b0 + q * 2 * (2 * NT) * 16, (2 * NT) * 16, 128);
-              const unsigned acc = (step != k0 || pass != 0 || q != 0) ? 1u : 0u;
-              asm volatile(
-                  "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-                  "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(dcol),
-                  "l"(da), "l"(db), "r"(idesc), "r"(acc)
-                  : "memory");
-            }
-          }
-          // the stage may be refilled once these UMMAs have read it
-          const unsigned mb = (unsigned)__cvta_generic_to_shared(&bar_empty[st]);
-          asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n" ::"r"(mb)
-                       : "memory");
-          if (step + 1 == k1) {
-            const unsigned mf = (unsigned)__cvta_generic_to_shared(&tmem_full[buf]);
-            asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n" ::"r"(mf)
-                         : "memory");
-          }
-        }
-      }
-    }
-  } else {
-    // ------------------------------------------------------------ epilogue group
-    const bool quad_ok = (D[W_FLAGS] & 16) != 0 && !accumulate && !atomic;
-    const int quad = warp & 3;  // TMEM lane quadrant of this warp
-    const int r = quad * 32 + lane;
-    for (unsigned j = 0; j < nw; ++j) {
-      const unsigned buf = j & 1;
-      mbar_wait(&tmem_full[buf], (j >> 1) & 1);
-      asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
-      const int slot = (int)(j % TI);
-      const long long baseC = ti_base[slot * 4 + 2];
-      const int m_valid = ti_valid[slot * 2 + 0], n_valid = ti_valid[slot * 2 + 1];
-      T* crow = C + baseC + offMC[r];
-      // 32 fp32 columns (16 complex) per tcgen05.ld: one TMEM round trip per 128 bytes of a row
-#pragma unroll 1
-      for (int col = 0; col < 2 * NT; col += 32) {  // fp32 column; complex column = col / 2
-        unsigned v[32];
-        const unsigned ta = taddr + buf * P::TMEM_COLS + ((unsigned)(quad * 32) << 16) + (unsigned)col;
-        asm volatile(
-            "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,"
-            "%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];\n"
-            : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
-              "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
-              "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
-              "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
-            : "r"(ta));
-        asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
-        if (r < m_valid) {
-#pragma unroll
-          for (int s4 = 0; s4 < 4; ++s4) {  // groups of 4 complex columns
-            const int c0 = (col >> 1) + s4 * 4;
-            const unsigned* w = v + s4 * 8;
-            if (c0 >= n_valid) continue;
-            if (quad_ok) {
-              const unsigned long long q0 = ((unsigned long long)w[1] << 32) | w[0], q1 = ((unsigned long long)w[3] << 32) | w[2];
-              const unsigned long long q2 = ((unsigned long long)w[5] << 32) | w[4], q3 = ((unsigned long long)w[7] << 32) | w[6];
-              asm volatile("st.global.v4.b64 [%0], {%1,%2,%3,%4};\n" ::"l"(crow + offNC[c0]), "l"(q0), "l"(q1), "l"(q2),
-                           "l"(q3)
-                           : "memory");
-            } else {
-#pragma unroll
-              for (int e = 0; e < 4; ++e) {
-                if (c0 + e < n_valid) {
-                  T* p = crow + offNC[c0 + e];
-                  const T val = make_float2(__uint_as_float(w[2 * e]), __uint_as_float(w[2 * e + 1]));
-                  if (atomic) {
-                    atomic_add_of(p, val);
-                  } else if (accumulate) {
-                    *p = add_of(*p, val);
-                  } else {
-                    *p = val;
-                  }
-                }
-              }
-            }
-          }
-        }
-      }
-      asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&tmem_empty[buf]);
-    }
-  }
-  named_sync<2, NCONS>();
-  if (warp == 0)
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(taddr), "r"(2 * P::TMEM_COLS)
-                 : "memory");
-}
 
 template <typename T, class P>
 __global__ void __launch_bounds__(P::THREADS + PRODUCER_THREADS, P::MIN_BLOCKS)
@@ -293,18 +106,13 @@ gett_kernel(const int64_t* __restrict__ D, const T* __restrict__ A, const T* __r
   long long* offNC = offMC + MT;
   long long* kbA = offNC + NT;
   long long* kbB = kbA + KCHUNK;
-  long long* ti_base = kbB + KCHUNK;  // [TI][4]: A, B, C, B'-tile index
+  long long* ti_base = kbB + KCHUNK;  // [TI][4]: A, B, C, -
   unsigned long long* bar_full = reinterpret_cast<unsigned long long*>(ti_base + 4 * TI);
   unsigned long long* bar_empty = bar_full + STAGES;
   unsigned* metaA = reinterpret_cast<unsigned*>(bar_empty + STAGES);
   unsigned* metaB = metaA + NA * NPROD;
   int* kval = reinterpret_cast<int*>(metaB + NB * NPROD);
   int* ti_valid = kval + KCHUNK;  // [TI][2]: m_valid, n_valid
-
-  __shared__ __align__(8) unsigned long long bar_tile_storage[4];  // tc05: tmem_full[2], tmem_empty[2]
-  __shared__ unsigned tmem_slot_storage;
-  [[maybe_unused]] unsigned long long* bar_tile = bar_tile_storage;
-  [[maybe_unused]] unsigned* tmem_slot = &tmem_slot_storage;
 
   const int tid = threadIdx.x;
   const int lane = tid & 31;
@@ -328,10 +136,6 @@ gett_kernel(const int64_t* __restrict__ D, const T* __restrict__ A, const T* __r
   auto digit_of = [&](unsigned idx, unsigned div, unsigned ext) -> unsigned {
     return g_pow2 ? ((idx >> (31 - __clz(div))) & (ext - 1)) : ((idx / div) % ext);
   };
-  // tcgen05 policy: A tile = contiguous runs of run_a elements fetched by TMA bulk copies (flags bit6)
-  [[maybe_unused]] const bool bulk_a =
-      P::IS_TC05 && (D[W_FLAGS] & 64) != 0 && (reinterpret_cast<unsigned long long>(A) & 15ull) == 0;
-  [[maybe_unused]] const unsigned run_a = (unsigned)D[W_RUNA];
   // no blocked (partial) dim touches the operand: every tabulated element is always valid
   const bool exactA = pgm < 0 && pgk < 0, exactB = pgn < 0 && pgk < 0;
 
@@ -357,13 +161,7 @@ gett_kernel(const int64_t* __restrict__ D, const T* __restrict__ A, const T* __r
   if (tid == 0) {
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(&bar_full[s], NPROD);
-      mbar_init(&bar_empty[s], P::IS_TC05 ? 1 : NCONS / 32);  // tc05: one tcgen05.commit per stage
-    }
-    if constexpr (P::IS_TC05) {
-      mbar_init(&bar_tile[0], 1);
-      mbar_init(&bar_tile[1], 1);
-      mbar_init(&bar_tile[2], 4);
-      mbar_init(&bar_tile[3], 4);
+      mbar_init(&bar_empty[s], NCONS / 32);
     }
     asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
   }
@@ -527,7 +325,6 @@ gett_kernel(const int64_t* __restrict__ D, const T* __restrict__ A, const T* __r
           ti_base[slot * 4 + 0] = a;
           ti_base[slot * 4 + 1] = b;
           ti_base[slot * 4 + 2] = c;
-          ti_base[slot * 4 + 3] = (long long)ib_ * tiles_n + in_;
           ti_valid[slot * 2 + 0] = pgm < 0 ? MTa : vm;
           ti_valid[slot * 2 + 1] = pgn < 0 ? NTa : vn;
           __threadfence_block();
@@ -535,7 +332,6 @@ gett_kernel(const int64_t* __restrict__ D, const T* __restrict__ A, const T* __r
       }
       named_sync<1, NPROD>();
       const long long tA = ti_base[slot * 4 + 0], tB = ti_base[slot * 4 + 1];
-      [[maybe_unused]] const long long tBp = ti_base[slot * 4 + 3];
       const unsigned m_valid = (unsigned)ti_valid[slot * 2 + 0], n_valid = (unsigned)ti_valid[slot * 2 + 1];
 
       for (unsigned step = k0; step < k1; ++step, ++g) {
@@ -561,31 +357,7 @@ gett_kernel(const int64_t* __restrict__ D, const T* __restrict__ A, const T* __r
         const T* srcA = A + tA + kbA[ti];
         const T* srcB = B + tB + kbB[ti];
         const unsigned kv = (unsigned)kval[ti];
-        bool arrived = false;
-        if constexpr (P::IS_TC05) {
-          if (bulk_a) {
-            // the A tile is a set of long contiguous runs: TMA bulk copies into the staging
-            // area (memory order); the MMA group scatters them into the UMMA layout
-            const unsigned bar = (unsigned)__cvta_generic_to_shared(&bar_full[st]);
-            const unsigned nruns = (unsigned)(MTa * KTa) / run_a;
-            const unsigned mine = ptid < nruns ? (nruns - ptid + NPROD - 1) / NPROD : 0u;
-            const unsigned bytes = mine * run_a * (unsigned)sizeof(T) + (ptid == 0 ? (unsigned)P::PAIR_BYTES : 0u);
-            asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.expect_tx.shared::cta.b64 st, [%0], %1;\n\t}\n" ::"r"(bar),
-                         "r"(bytes)
-                         : "memory");
-            T* stg = dA + 2 * P::MT * P::KT;
-            for (unsigned q = ptid; q < nruns; q += NPROD) {
-              const unsigned dst = (unsigned)__cvta_generic_to_shared(stg + q * run_a);
-              asm volatile(
-                  "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::"r"(dst),
-                  "l"(srcA + gA[q * run_a]), "r"(run_a * (unsigned)sizeof(T)), "r"(bar)
-                  : "memory");
-            }
-            arrived = true;
-          }
-        }
-        if (arrived) {
-        } else if (exactA) {
+        if (exactA) {
 #pragma unroll
           for (int i = 0; i < NA; ++i) {
             const unsigned meta = metaA[i * NPROD + ptid];
@@ -602,22 +374,7 @@ gett_kernel(const int64_t* __restrict__ D, const T* __restrict__ A, const T* __r
             }
           }
         }
-        if constexpr (P::IS_TC05) {
-          // the stage's B'hi + B'lo tiles are contiguous in the prepared buffer: one TMA bulk copy
-          if (ptid == 0) {
-            const unsigned bar = (unsigned)__cvta_generic_to_shared(&bar_full[st]);
-            const unsigned dst = (unsigned)__cvta_generic_to_shared(dB);
-            const char* src = reinterpret_cast<const char*>(B) +
-                              ((unsigned long long)tBp * steps_k + step) * (unsigned long long)P::PAIR_BYTES;
-            if (!arrived)  // (bulk mode already announced these bytes with its arrival)
-              asm volatile("mbarrier.expect_tx.relaxed.cta.shared::cta.b64 [%0], %1;\n" ::"r"(bar), "r"(P::PAIR_BYTES)
-                           : "memory");
-            asm volatile(
-                "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::"r"(dst),
-                "l"(src), "r"(P::PAIR_BYTES), "r"(bar)
-                : "memory");
-          }
-        } else if (exactB) {
+        if (exactB) {
 #pragma unroll
           for (int i = 0; i < NB; ++i) {
             const unsigned meta = metaB[i * NPROD + ptid];
@@ -634,18 +391,13 @@ gett_kernel(const int64_t* __restrict__ D, const T* __restrict__ A, const T* __r
             }
           }
         }
-        if (!arrived) mbar_arrive_cp_async(&bar_full[st]);
+        mbar_arrive_cp_async(&bar_full[st]);
       }
     }
     cp_async_commit();
     cp_async_wait<0>();  // do not exit with copies in flight
   } else {
     // ===================================================== CONSUMER WARPS
-    if constexpr (P::IS_TC05) {
-      tc05_consumer<T, P>(D, C, sA, sB, bar_full, bar_empty, bar_tile, tmem_slot, ti_base, ti_valid, offMC, offNC, nw,
-                          tiles_all, steps_k, steps_per_split, accumulate, atomic, metaA, bulk_a, exactA);
-      return;
-    }
     if constexpr (P::CONSUMER_REGS > 0) reg_alloc<P::CONSUMER_REGS>();
     // valid k of a step: only a blocked (partial) k dim can shorten it
     const unsigned pk_div = pgk >= 0 ? (unsigned)D[OFF_GK + pgk * 4 + 1] : 1u;

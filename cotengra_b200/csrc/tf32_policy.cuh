@@ -44,8 +44,6 @@ struct Tf32Policy {
   static constexpr int SCRATCH_ELEMS = 0;
   static constexpr int CONSUMER_REGS = (THREADS == 256) ? 232 : 0, PRODUCER_REGS = 40;
   static constexpr bool HAS_BCACHE = false;
-  static constexpr bool IS_TC05 = false;
-  static constexpr int A_GATHER = A_ELEMS, B_GATHER = B_ELEMS;
   static constexpr int MIN_BLOCKS = 1;
   static_assert(KT % 8 == 0, "KT must be a multiple of the MMA k");
   struct Acc {
