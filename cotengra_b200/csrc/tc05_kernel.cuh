@@ -16,10 +16,15 @@
 //   warp   12    B' producer   one TMA bulk copy per k-step of the prepared B'hi|B'lo
 //                              pair (ring of NB slots fed from L2; when all the B' tiles a
 //                              CTA ever needs fit the ring they are loaded once and stay).
-//   warps  0-3   scatter/MMA   staging -> A'hi / A'lo in UMMA's K-major core-matrix
-//                              layout (double buffered), then ONE thread issues the 12
-//                              UMMAs of the step and commits them to the "operand free",
-//                              "B' stage free" and (last step) "accumulator full" barriers.
+//   warps  0-3   scatter       staging -> A'hi / A'lo in UMMA's K-major core-matrix
+//                              layout (double buffered A' images).
+//   warp   13    MMA issuer    a whole warp runs the issue loop with warp-uniform control
+//                              flow (descriptors stay in uniform registers); one elected
+//                              lane issues the 12 UMMAs of a k-step and commits them to the
+//                              "operand free", "B' slot free" and (last step) "accumulator
+//                              full" barriers.  Kept apart from the scatter warps: the
+//                              issue sequence costs ~1300 clk per step when it runs
+//                              divergently inside them (ncu, profiles/).
 //   warps  4-7   epilogue      TMEM -> registers -> C (32-byte row sectors) for tile j-1
 //                              while the MMAs of tile j run (two TMEM accumulators).
 //
@@ -40,8 +45,8 @@ struct Tc05Cfg {
   static constexpr int OP_BYTES = 8 * (LBO_BASE + 64);     // one A' image with the largest padding
   static constexpr int TMEM_COLS = 2 * NT;                 // fp32 columns of one accumulator
   static constexpr int TI = SA_MAX + 4;                    // tile-info ring (epilogue lags <= 2 tiles)
-  static constexpr int NBARS = 2 * SA_MAX + 2 * NB_MAX + 2 + 4;
-  static constexpr int THREADS = 13 * 32;
+  static constexpr int NBARS = 2 * SA_MAX + 2 * NB_MAX + 2 + 2 + 4;
+  static constexpr int THREADS = 14 * 32;
   static_assert(TMEM_COLS == 64 || TMEM_COLS == 128, "two accumulators must fit 512 TMEM columns");
   static constexpr size_t fixed_bytes() {  // everything but the two rings
     return 4 * (size_t)OP_BYTES + 8 * (size_t)(MT + NT + KCHUNK + 4 * TI + NBARS) + 128;
@@ -50,6 +55,13 @@ struct Tc05Cfg {
     return fixed_bytes() + (size_t)sa * A_TILE * 8 + (size_t)nb * PAIR_BYTES;
   }
 };
+
+// one lane of a converged warp (the compiler keeps the surrounding code warp-uniform)
+__device__ __forceinline__ bool elect_one() {
+  unsigned pred;
+  asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}\n" : "=r"(pred));
+  return pred != 0;
+}
 
 // ring position + phase bit of an mbarrier ring
 struct RingPos {
@@ -66,7 +78,7 @@ struct RingPos {
 // CTA never change (one batch, grid a multiple of tiles_n, steps_k <= NB): they are
 // loaded once into slot = k-step and stay resident.
 template <int NT>
-__global__ void __launch_bounds__(416, 1)
+__global__ void __launch_bounds__(448, 1)
 tc05_kernel(const int64_t* __restrict__ D, const float2* __restrict__ A, const float* __restrict__ Bp,
             float2* __restrict__ C, const unsigned SA, const unsigned NB, const int b_stat) {
   using Cfg = Tc05Cfg<NT>;
@@ -86,7 +98,8 @@ tc05_kernel(const int64_t* __restrict__ D, const float2* __restrict__ A, const f
   unsigned long long* b_full = stg_empty + Cfg::SA_MAX;
   unsigned long long* b_empty = b_full + Cfg::NB_MAX;
   unsigned long long* op_empty = b_empty + Cfg::NB_MAX;  // [2] one tcgen05.commit
-  unsigned long long* tmem_full = op_empty + 2;  // [2] one tcgen05.commit
+  unsigned long long* op_full = op_empty + 2;    // [2] four scatter warps
+  unsigned long long* tmem_full = op_full + 2;   // [2] one tcgen05.commit
   unsigned long long* tmem_empty = tmem_full + 2;  // [2] four epilogue warps
   __shared__ unsigned tmem_slot;
 
@@ -143,6 +156,8 @@ tc05_kernel(const int64_t* __restrict__ D, const float2* __restrict__ A, const f
     }
     mbar_init(&op_empty[0], 1);
     mbar_init(&op_empty[1], 1);
+    mbar_init(&op_full[0], 4);
+    mbar_init(&op_full[1], 4);
     mbar_init(&tmem_full[0], 1);
     mbar_init(&tmem_full[1], 1);
     mbar_init(&tmem_empty[0], 4);
@@ -200,7 +215,7 @@ tc05_kernel(const int64_t* __restrict__ D, const float2* __restrict__ A, const f
   const unsigned steps_per_split = (steps_k + splitk - 1) / splitk;
   const unsigned nw = blockIdx.x < total_work ? (total_work - blockIdx.x + gridDim.x - 1) / gridDim.x : 0u;
   auto work_krange = [&](unsigned j, unsigned& k0, unsigned& k1) {
-    const unsigned ks = (blockIdx.x + j * gridDim.x) / tiles_all;
+    const unsigned ks = splitk > 1 ? (blockIdx.x + j * gridDim.x) / tiles_all : 0u;
     k0 = ks * steps_per_split;
     k1 = min(steps_k, k0 + steps_per_split);
   };
@@ -320,24 +335,18 @@ tc05_kernel(const int64_t* __restrict__ D, const float2* __restrict__ A, const f
       }
     }
   } else if (warp < 4) {
-    // ===================================================== SCATTER / MMA GROUP
-    // InstrDescriptor: D=f32 [4,6)=1, A=tf32 [7,10)=2, B=tf32 [10,13)=2, K-major A/B, N>>3 [17,23), M>>4 [24,29)
-    constexpr unsigned idesc =
-        (1u << 4) | (2u << 7) | (2u << 10) | ((unsigned)(Cfg::TMEM_COLS >> 3) << 17) | ((unsigned)(MT >> 4) << 24);
+    // ===================================================== SCATTER GROUP
     constexpr int NSCAT = A_TILE / GROUP;
     unsigned upos[NSCAT];
 #pragma unroll
     for (int i = 0; i < NSCAT; ++i) upos[i] = a_pos((unsigned)(tid + i * GROUP));
     unsigned g = 0;
-    RingPos ra, rb;
+    RingPos ra;
     for (unsigned j = 0; j < nw; ++j) {
       unsigned k0, k1;
       work_krange(j, k0, k1);
-      const unsigned buf = j & 1;
-      mbar_wait(&tmem_empty[buf], ((j >> 1) & 1) ^ 1);  // epilogue of tile j-2 has drained this accumulator
-      asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
-      for (unsigned step = k0; step < k1; ++step, ++g, ra.next(SA), rb.next(NB)) {
-        const unsigned sa = ra.idx, sb = b_stat ? step : rb.idx, ob = g & 1;
+      for (unsigned step = k0; step < k1; ++step, ++g, ra.next(SA)) {
+        const unsigned sa = ra.idx, ob = g & 1;
         float2* hi2 = reinterpret_cast<float2*>(op + (size_t)(ob * 2) * Cfg::OP_BYTES);
         float2* lo2 = reinterpret_cast<float2*>(op + (size_t)(ob * 2 + 1) * Cfg::OP_BYTES);
         const float2* src = stg + (size_t)sa * A_TILE;
@@ -351,21 +360,39 @@ tc05_kernel(const int64_t* __restrict__ D, const float2* __restrict__ A, const f
         }
         asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");  // generic-proxy writes -> tensor core
         __syncwarp();
-        if (lane == 0) mbar_arrive(&stg_empty[sa]);  // this warp's reads of the staging tile are done
-        asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
-        named_sync<3, GROUP>();
+        if (lane == 0) {
+          mbar_arrive(&stg_empty[sa]);  // this warp's reads of the staging tile are done
+          mbar_arrive(&op_full[ob]);    // ... and its part of the A' images is written
+        }
+      }
+    }
+  } else if (warp == 13) {
+    // ===================================================== MMA ISSUER (warp-uniform loop)
+    // InstrDescriptor: D=f32 [4,6)=1, A=tf32 [7,10)=2, B=tf32 [10,13)=2, K-major A/B, N>>3 [17,23), M>>4 [24,29)
+    constexpr unsigned idesc =
+        (1u << 4) | (2u << 7) | (2u << 10) | ((unsigned)(Cfg::TMEM_COLS >> 3) << 17) | ((unsigned)(MT >> 4) << 24);
+    const unsigned op_base = (unsigned)__cvta_generic_to_shared(op);
+    const unsigned b_base = (unsigned)__cvta_generic_to_shared(sB);
+    unsigned g = 0;
+    RingPos rb;
+    for (unsigned j = 0; j < nw; ++j) {
+      unsigned k0, k1;
+      work_krange(j, k0, k1);
+      const unsigned buf = j & 1;
+      mbar_wait(&tmem_empty[buf], ((j >> 1) & 1) ^ 1);  // epilogue of tile j-2 has drained this accumulator
+      for (unsigned step = k0; step < k1; ++step, ++g, rb.next(NB)) {
+        const unsigned ob = g & 1, sb = b_stat ? step : rb.idx;
+        mbar_wait(&op_full[ob], (g >> 1) & 1);
+        if (!b_stat) {
+          mbar_wait(&b_full[sb], rb.ph);
+        } else if (j == 0) {
+          mbar_wait(&b_full[sb], 0);  // resident B': filled once
+        }
         asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
-        if (tid == 0) {
-          if (!b_stat) {
-            mbar_wait(&b_full[sb], rb.ph);
-          } else if (j == 0) {
-            mbar_wait(&b_full[sb], 0);  // resident B': filled once
-          }
-          const unsigned a_hi = (unsigned)__cvta_generic_to_shared(hi2);
-          const unsigned a_lo = (unsigned)__cvta_generic_to_shared(lo2);
-          const unsigned b_hi = (unsigned)__cvta_generic_to_shared(sB + (size_t)sb * Cfg::PAIR_BYTES);
-          const unsigned b_lo = b_hi + Cfg::TILE_FLOATS * 4;
-          const unsigned dcol = taddr + buf * Cfg::TMEM_COLS;
+        const unsigned a_hi = op_base + (ob * 2) * (unsigned)Cfg::OP_BYTES, a_lo = a_hi + (unsigned)Cfg::OP_BYTES;
+        const unsigned b_hi = b_base + sb * (unsigned)Cfg::PAIR_BYTES, b_lo = b_hi + Cfg::TILE_FLOATS * 4;
+        const unsigned dcol = taddr + buf * Cfg::TMEM_COLS;
+        if (elect_one()) {
 #pragma unroll
           for (int pass = 0; pass < 3; ++pass) {
             const unsigned a0 = pass == 0 ? a_lo : a_hi, b0 = pass == 1 ? b_lo : b_hi;  // lo*hi, hi*lo, hi*hi
@@ -383,21 +410,23 @@ tc05_kernel(const int64_t* __restrict__ D, const float2* __restrict__ A, const f
             }
           }
           const unsigned m_op = (unsigned)__cvta_generic_to_shared(&op_empty[ob]);
-          const unsigned m_b = (unsigned)__cvta_generic_to_shared(&b_empty[sb]);
           asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n" ::"r"(m_op)
                        : "memory");
-          if (!b_stat)
+          if (!b_stat) {
+            const unsigned m_b = (unsigned)__cvta_generic_to_shared(&b_empty[sb]);
             asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n" ::"r"(m_b)
                          : "memory");
+          }
           if (step + 1 == k1) {
             const unsigned mf = (unsigned)__cvta_generic_to_shared(&tmem_full[buf]);
             asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n" ::"r"(mf)
                          : "memory");
           }
         }
+        __syncwarp();
       }
     }
-  } else {
+  } else if (warp < 8) {
     // ===================================================== EPILOGUE GROUP (warps 4-7)
     const bool quad_ok = (D[W_FLAGS] & 16) != 0 && !accumulate && !atomic &&
                          (reinterpret_cast<unsigned long long>(C) & 31ull) == 0;
