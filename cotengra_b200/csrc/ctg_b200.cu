@@ -234,6 +234,7 @@ int launch_gett_typed(const int64_t* h, const int64_t* d, const void* A, const v
   if constexpr (std::is_same<T, float2>::value) {
     if (variant == VAR_TC05_128x64) return launch_tc05<64>(h, d, A, B, C, st);
     if (variant == VAR_TC05_128x32) return launch_tc05<32>(h, d, A, B, C, st);
+    if (variant == VAR_TC05_128x16) return launch_tc05<16>(h, d, A, B, C, st);
   }
   switch (variant) {
     case VAR_SIMT_64x64: return launch_gett_policy<T, SimtPolicy<T, 64, 64, 8, 3>>(h, d, A, B, C, st);
@@ -248,6 +249,13 @@ int launch_gett_typed(const int64_t* h, const int64_t* d, const void* A, const v
       case VAR_DMMA_64x128: return launch_gett_policy<T, DmmaPolicy<T, 2, 4, 4, 4, 16, 3>>(h, d, A, B, C, st);
       case VAR_DMMA_256x32: return launch_gett_policy<T, DmmaPolicy<T, 8, 1, 4, 4, 8, 4>>(h, d, A, B, C, st);
       case VAR_DMMA_256x16: return launch_gett_policy<T, DmmaPolicy<T, 8, 1, 4, 2, 8, 5>>(h, d, A, B, C, st);
+      default: break;
+    }
+  }
+  if constexpr (sizeof(T) == 16) {
+    switch (variant) {
+      case VAR_DMMA3M_128x32: return launch_gett_policy<T, DmmaPolicy<T, 4, 2, 4, 2, 16, 4, true>>(h, d, A, B, C, st);
+      case VAR_DMMA3M_256x16: return launch_gett_policy<T, DmmaPolicy<T, 8, 1, 4, 2, 8, 5, true>>(h, d, A, B, C, st);
       default: break;
     }
   }

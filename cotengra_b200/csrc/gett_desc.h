@@ -70,7 +70,10 @@ enum : int {
   VAR_ROW_256x4 = 7,   // same, N <= 4 (fewer registers -> more resident CTAs)
   VAR_ROWSTREAM = 8,   // N, K <= 8, exact tiles, no batch: thread-per-row straight from global memory
   VAR_TC05_128x64 = 9, // complex64, exact 128 x 64 x 16 tiles: tcgen05.mma kind::tf32 (3 passes), TMEM accumulators
-  VAR_TC05_128x32 = 10
+  VAR_TC05_128x32 = 10,
+  VAR_TC05_128x16 = 11,
+  VAR_DMMA3M_128x32 = 12,  // complex128, 3M complex product (three DMMAs per fragment pair)
+  VAR_DMMA3M_256x16 = 13
 };
 
 // ---- single-operand descriptor (cotengra/contract.py:332-361) -------------

@@ -47,7 +47,8 @@ struct Tc05Cfg {
   static constexpr int TI = SA_MAX + 4;                    // tile-info ring (epilogue lags <= 2 tiles)
   static constexpr int NBARS = 2 * SA_MAX + 2 * NB_MAX + 2 + 2 + 4;
   static constexpr int THREADS = 14 * 32;
-  static_assert(TMEM_COLS == 64 || TMEM_COLS == 128, "two accumulators must fit 512 TMEM columns");
+  static_assert(TMEM_COLS == 32 || TMEM_COLS == 64 || TMEM_COLS == 128,
+                "two accumulators: a power of two >= 32 columns each, <= 512 together");
   static constexpr size_t fixed_bytes() {  // everything but the two rings
     return 4 * (size_t)OP_BYTES + 8 * (size_t)(MT + NT + KCHUNK + 4 * TI + NBARS) + 128;
   }

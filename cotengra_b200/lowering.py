@@ -58,7 +58,9 @@ SDESC_MAGIC = 0x4354474253303031
 
 VAR_SIMT_64x64, VAR_KRED, VAR_DMMA_128x64, VAR_DMMA_64x128, VAR_DMMA_256x32 = 0, 1, 2, 3, 4
 VAR_DMMA_256x16, VAR_ROW_128x8, VAR_ROW_256x4, VAR_ROWSTREAM = 5, 6, 7, 8
-VAR_TC05_128x64, VAR_TC05_128x32 = 9, 10
+VAR_TC05_128x64, VAR_TC05_128x32, VAR_TC05_128x16 = 9, 10, 11
+VAR_DMMA3M_128x32, VAR_DMMA3M_256x16 = 12, 13
+TC05_VARIANTS = (VAR_TC05_128x64, VAR_TC05_128x32, VAR_TC05_128x16)
 # (MT, NT, KT) of every kernel variant -- must match ctg_b200.cu's dispatch
 VARIANT_TILES = {
     VAR_SIMT_64x64: (64, 64, 8),
@@ -72,6 +74,9 @@ VARIANT_TILES = {
     VAR_ROWSTREAM: (256, 8, 8),
     VAR_TC05_128x64: (128, 64, 16),
     VAR_TC05_128x32: (128, 32, 16),
+    VAR_TC05_128x16: (128, 16, 16),
+    VAR_DMMA3M_128x32: (128, 32, 16),
+    VAR_DMMA3M_256x16: (256, 16, 8),
 }
 
 DTYPE_CODES = {"float32": 0, "float64": 1, "complex64": 2, "complex128": 3}
@@ -318,7 +323,7 @@ class PairPlan:
     splitk: int
 
 
-def choose_variant(dtype, B, M, N, K, allow_dmma=True, allow_stream=True, allow_tc05=True):
+def choose_variant(dtype, B, M, N, K, allow_dmma=True, allow_stream=True, allow_tc05=True, allow_3m=False):
     if M == 1 and N == 1 and B == 1 and K >= 8192:
         return VAR_KRED
     if N <= 8 and K <= 8 and B == 1 and 64 <= M < 1 << 32 and allow_stream:
@@ -330,10 +335,18 @@ def choose_variant(dtype, B, M, N, K, allow_dmma=True, allow_stream=True, allow_
             and K <= 256 and M * N * K >= 1 << 20):
         if N % 64 == 0:
             return VAR_TC05_128x64
-        if N == 32:
+        if N % 32 == 0:
             return VAR_TC05_128x32
+        if N % 16 == 0:
+            return VAR_TC05_128x16
     # tensor-core tiles: fp64 DMMA for float64/complex128, 3xTF32 for float32/complex64
     if allow_dmma and M * N * K >= 1 << 15 and M * N >= 1024:
+        if dtype == "complex128" and allow_3m and N >= 64 and K >= 64:
+            # 3M complex product (opt-in): 25 % fewer DMMAs but narrower tiles (accumulator
+            # registers).  Measured on B200: 36.6-37.8 vs 33.6 TFLOP/s at N=128 K=64, but 14 vs
+            # 24 at N=128 K=16 (per-tile epilogue dominates) and no gain on the whole Sycamore
+            # slice (160.5 vs 159 ms), so the default stays the 4-DMMA product.
+            return VAR_DMMA3M_128x32
         if N >= 96:
             return VAR_DMMA_64x128
         if N >= 48:
@@ -365,6 +378,9 @@ def build_pair_desc(dims: PairDims, dtype, accumulate=False, sm_count=148,
 
     if variant is None:
         variant = choose_variant(dtype, B, M, N, K, allow_dmma)
+    if variant in (VAR_DMMA3M_128x32, VAR_DMMA3M_256x16) and dtype != "complex128":
+        # the 3M identity is a complex128 kernel: other dtypes take the plain tensor-core tiles
+        variant = VAR_DMMA_256x32 if variant == VAR_DMMA3M_128x32 else VAR_DMMA_256x16
     if variant == VAR_ROWSTREAM:
         # the streaming kernel needs exact tiles: every m dim must divide
         ok = N <= 8 and K <= 8 and B == 1 and M < 1 << 32 and all(
@@ -373,7 +389,7 @@ def build_pair_desc(dims: PairDims, dtype, accumulate=False, sm_count=148,
             variant = VAR_ROW_256x4 if N <= 4 else VAR_ROW_128x8
     MT, NT, KT = VARIANT_TILES[variant]
 
-    if variant in (VAR_TC05_128x64, VAR_TC05_128x32):
+    if variant in TC05_VARIANTS:
         # tcgen05: every thread of the epilogue owns a whole row, so the rows of a tile need
         # not be neighbours in C -- pick them for the longest contiguous runs of A instead
         # (and B is re-packed by bprime_kernel anyway: only A's strides matter for k too)
@@ -465,7 +481,7 @@ def build_pair_desc(dims: PairDims, dtype, accumulate=False, sm_count=148,
     is_p2 = lambda e: e > 0 and (e & (e - 1)) == 0  # noqa: E731
     grid_pow2 = all(is_p2(g[0]) for g in gm + gn + gb)
     m_pow2 = all(is_p2(d[0]) for d in tm) and all(is_p2(g[0]) for g in gm)
-    if variant in (VAR_TC05_128x64, VAR_TC05_128x32):
+    if variant in TC05_VARIANTS:
         # the tcgen05 kernel only takes exact tiles of its native shape
         exact = (MTa, NTa, KTa) == (MT, NT, KT) and dtype == "complex64" and all(
             p is None or p[1] % p[2] == 0 for p in (pm, pn, pk))
@@ -483,7 +499,7 @@ def build_pair_desc(dims: PairDims, dtype, accumulate=False, sm_count=148,
     # 8-byte element types: groups of 4 (bit4) / 2 (bit5) columns adjacent in C and
     # 32- / 16-byte aligned -> vector row stores in the streaming row kernel
     def _cols_ok(g):
-        if variant in (VAR_TC05_128x64, VAR_TC05_128x32):
+        if variant in TC05_VARIANTS:
             # exact tiles: only the leading columns of a tile row have to be adjacent
             run = 1
             for d in tn:
@@ -503,7 +519,7 @@ def build_pair_desc(dims: PairDims, dtype, accumulate=False, sm_count=148,
     # tcgen05 variants: if the A tile is made of long contiguous runs (dense prefix of
     # the load order), the producers fetch whole runs with TMA bulk copies (bit6)
     run_a, bulk_a = 1, False
-    if variant in (VAR_TC05_128x64, VAR_TC05_128x32):
+    if variant in TC05_VARIANTS:
         for r_ in lda:
             if r_[1] != run_a:
                 break

@@ -105,7 +105,8 @@ def test_tensordot_golden_shapes():
 
 
 @pytest.mark.parametrize("variant", [L.VAR_SIMT_64x64, L.VAR_DMMA_128x64, L.VAR_DMMA_64x128,
-                                     L.VAR_DMMA_256x32, L.VAR_DMMA_256x16, L.VAR_ROW_128x8, L.VAR_ROW_256x4, L.VAR_ROWSTREAM, L.VAR_TC05_128x64, L.VAR_TC05_128x32])
+                                     L.VAR_DMMA_256x32, L.VAR_DMMA_256x16, L.VAR_ROW_128x8, L.VAR_ROW_256x4, L.VAR_ROWSTREAM, L.VAR_TC05_128x64, L.VAR_TC05_128x32, L.VAR_TC05_128x16,
+                                     L.VAR_DMMA3M_128x32, L.VAR_DMMA3M_256x16])
 @pytest.mark.parametrize("dtype", ["complex128", "float64", "complex64", "float32"])
 def test_every_kernel_variant_ragged_gemm(variant, dtype):
     import torch
@@ -128,7 +129,7 @@ def test_every_kernel_variant_ragged_gemm(variant, dtype):
             (m, n, k, variant, dtype)
 
 
-_T64, _T32 = L.VAR_TC05_128x64, L.VAR_TC05_128x32
+_T64, _T32, _T16 = L.VAR_TC05_128x64, L.VAR_TC05_128x32, L.VAR_TC05_128x16
 TC05_CASES = [
     # (name, eq, shapes, build_pair_desc kwargs)
     ("ring_b_long_k", "ab,bc->ac", [(1024, 256), (256, 64)], {"force_splitk": 1}),       # 16 k-steps > resident slots
@@ -141,6 +142,8 @@ TC05_CASES = [
     ("non_pow2_grid", "ab,bc->ac", [(384, 48), (48, 32)], {"variant": _T32, "force_splitk": 1}),   # 3 tiles x 3 k-steps
     ("permuted_out", "aibj,ijc->cba", [(16, 4, 16, 8), (4, 8, 64)], {"variant": _T64}),  # strided C rows and columns
     ("wide_n", "ab,bc->ac", [(1024, 64), (64, 512)], {"force_splitk": 1}),               # 8 column tiles: resident B' per CTA
+    ("narrow_n16", "ab,cb->ac", [(4096, 32), (16, 32)], {}),                             # 128 x 16 tiles (UMMA N = 32)
+    ("narrow_n16_batched", "xab,xbc->xca", [(2, 512, 64), (2, 64, 16)], {"variant": _T16}),
 ]
 
 
@@ -161,7 +164,7 @@ def test_tcgen05_kernel_modes(case, misalign):
     out_shape = tuple(dict(zip(ta_ + tb_, a.shape + b.shape))[ix] for ix in out)
     n_out = math.prod(out_shape)
     plan = L.build_pair_desc(dims, "complex64", c_dense_elems=n_out, sm_count=_lib.device_info()["sm_count"], **kw)
-    assert plan.variant in (L.VAR_TC05_128x64, L.VAR_TC05_128x32), (name, plan.variant)
+    assert plan.variant in L.TC05_VARIANTS, (name, plan.variant)
     bulk = bool(plan.words[L.W_FLAGS] & 64)
     assert bulk == (name != "gather_odd_strides")
     if "force_splitk" in kw:
