@@ -353,11 +353,15 @@ tc05_kernel(const int64_t* __restrict__ D, const float2* __restrict__ A, const f
         const float2* src = stg + (size_t)sa * A_TILE;
         mbar_wait(&op_empty[ob], ((g >> 1) & 1) ^ 1);  // the UMMAs of step g-2 have read these images
         mbar_wait(&stg_full[sa], ra.ph);
+        // all loads first: the compiler cannot prove the A' images do not alias the staging
+        // tile and would otherwise serialise LDS -> STS -> LDS ...
+        float2 v[NSCAT];
+#pragma unroll
+        for (int i = 0; i < NSCAT; ++i) v[i] = src[tid + i * GROUP];
 #pragma unroll
         for (int i = 0; i < NSCAT; ++i) {
-          const float2 v = src[tid + i * GROUP];
-          hi2[upos[i]] = v;  // the tensor core truncates its operands to tf32 itself
-          lo2[upos[i]] = make_float2(v.x - trunc_tf32(v.x), v.y - trunc_tf32(v.y));
+          hi2[upos[i]] = v[i];  // the tensor core truncates its operands to tf32 itself
+          lo2[upos[i]] = make_float2(v[i].x - trunc_tf32(v[i].x), v[i].y - trunc_tf32(v[i].y));
         }
         asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");  // generic-proxy writes -> tensor core
         __syncwarp();
