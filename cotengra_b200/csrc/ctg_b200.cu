@@ -62,6 +62,13 @@ DevInfo& devinfo() {
       d.minor = p.minor;
       d.smem_optin = p.sharedMemPerBlockOptin;
       cached_dev = dev;
+      // the tcgen05 launches take their B' scratch from the stream-ordered pool: keep freed
+      // blocks cached across synchronisation points instead of returning them to the driver
+      cudaMemPool_t pool;
+      if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+        uint64_t keep = UINT64_MAX;
+        cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+      }
     } else {
       d.ok = false;
     }
