@@ -1,6 +1,6 @@
 """Standalone benchmark of the heaviest nodes of one Sycamore-m20 slice (dev tool).
 
-usage: python scripts/gpu_node_bench.py [dtype] [topk] [--ncu]
+usage: python scripts/gpu_node_bench.py [dtype] [topk] [--ncu] [--rows] [--mnk=M,N,K]
 Each selected node is launched alone through ctgb_contract_pair on dummy
 operands of the right size, timed with CUDA events; with --ncu one launch per
 node is bracketed by cudaProfilerStart/Stop (run under
@@ -20,6 +20,7 @@ dtype = sys.argv[1] if len(sys.argv) > 1 else "complex128"
 topk = int(sys.argv[2]) if len(sys.argv) > 2 else 8
 use_ncu = "--ncu" in sys.argv
 rows_only = "--rows" in sys.argv
+mnk = next((tuple(int(x) for x in a.split("=")[1].split(",")) for a in sys.argv if a.startswith("--mnk=")), None)
 rec = next(r for r in load_json("sycamore_m20.json") if r["name"] == "sycamore_m20_appxB")
 spec = cb.TreeSpec(rec["inputs"], rec["output"], rec["size_dict"], rec["path"], decode_sliced(rec["sliced"]))
 plan = cb.ExecPlan(spec.contractions(), spec.inputs, spec.output, spec.size_dict, spec.sliced, dtype=dtype,
@@ -35,6 +36,8 @@ def weight(nd):
     el = sum(int(np.prod(x.shape)) for x in (nd["a"], nd["b"], nd["c"]))
     return el * es / 6.4e12 + 8 * B * M * N * K / 37e12
 nodes.sort(key=lambda nd: -weight(nd))
+if mnk:
+    nodes = [nd for nd in nodes if tuple(nd["sizes"][1:]) == mnk]
 seen, picked = set(), []
 for nd in nodes:
     key = (nd["sizes"], int(nd["plan"].variant))
