@@ -153,8 +153,8 @@ int launch_rowstream(const int64_t* h, const int64_t* d, const void* A, const vo
   T* c = (T*)C;
   if (N <= 4 && K <= 4)
     rowstream_kernel<T, 4, 4, true><<<(unsigned)blocks, 256, 0, st>>>(d, a, b, c);
-  else if (N <= 2)
-    rowstream_kernel<T, 2, 8, true><<<(unsigned)blocks, 256, 0, st>>>(d, a, b, c);
+  else if (N <= 2)  // (B from shared memory: in registers it costs 154 registers = one block / SM)
+    rowstream_kernel<T, 2, 8, sizeof(T) < 16><<<(unsigned)blocks, 256, 0, st>>>(d, a, b, c);
   else
     rowstream_kernel<T, 8, 8, false><<<(unsigned)blocks, 256, 0, st>>>(d, a, b, c);
   g_launches.fetch_add(1, std::memory_order_relaxed);

@@ -12,7 +12,7 @@
 constexpr int RS_MAXDIMS = MAX_T + MAX_G;
 
 template <typename T, int NMAX, int KMAX, bool BREG>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, BREG ? 2 : 3)
 rowstream_kernel(const int64_t* __restrict__ D, const T* __restrict__ A, const T* __restrict__ B, T* __restrict__ C) {
   __shared__ long long s_akoff[KMAX], s_bkoff[KMAX], s_bnoff[NMAX], s_cnoff[NMAX];
   __shared__ long long s_msA[RS_MAXDIMS], s_msC[RS_MAXDIMS];
@@ -131,59 +131,69 @@ rowstream_kernel(const int64_t* __restrict__ D, const T* __restrict__ A, const T
 #pragma unroll
       for (int kk = 0; kk < KMAX; ++kk)
         if (kk < K) a[i][kk] = A[oa[i] + akoff[kk]];
+    // columns in chunks of CH: 16-byte types with 8 columns would otherwise hold 8 accumulators
+    // + 8 operand elements per row (114 registers, 2 blocks / SM; ncu: 25 % of the warps resident,
+    // short-scoreboard bound) -- 4 + 8 fit three blocks
+    constexpr int CH = (NMAX > 4 && sizeof(T) >= 16) ? 4 : NMAX;
 #pragma unroll
     for (int i = 0; i < R; ++i) {
-      T acc[NMAX];
-#pragma unroll
-      for (int c = 0; c < NMAX; ++c) acc[c] = zero_of<T>();
-#pragma unroll
-      for (int kk = 0; kk < KMAX; ++kk) {
-        if (kk < K) {
-#pragma unroll
-          for (int c = 0; c < NMAX; ++c) {
-            if constexpr (BREG) {
-              mac(acc[c], a[i][kk], breg[kk][c]);
-            } else {
-              if (c < N) mac(acc[c], a[i][kk], s_B[kk * NMAX + c]);
-            }
-          }
-        }
-      }
       if (!live[i]) continue;
       T* pc = C + oc[i];
-      if constexpr (sizeof(T) == 8) {
-        if (quad8) {
 #pragma unroll
-          for (int c = 0; c + 3 < NMAX; c += 4)
-            if (c < N) {
-              const unsigned long long* q = reinterpret_cast<const unsigned long long*>(&acc[c]);
-              asm volatile("st.global.v4.b64 [%0], {%1,%2,%3,%4};" ::"l"(pc + s_cnoff[c]), "l"(q[0]), "l"(q[1]),
-                           "l"(q[2]), "l"(q[3])
-                           : "memory");
+      for (int c0 = 0; c0 < NMAX; c0 += CH) {
+        if (c0 >= N) break;
+        T acc[CH];
+#pragma unroll
+        for (int c = 0; c < CH; ++c) acc[c] = zero_of<T>();
+#pragma unroll
+        for (int kk = 0; kk < KMAX; ++kk) {
+          if (kk < K) {
+#pragma unroll
+            for (int c = 0; c < CH; ++c) {
+              if constexpr (BREG) {
+                mac(acc[c], a[i][kk], breg[kk][c0 + c]);
+              } else {
+                if (c0 + c < N) mac(acc[c], a[i][kk], s_B[kk * NMAX + c0 + c]);
+              }
             }
-          continue;
-        }
-        if (pair8) {
-#pragma unroll
-          for (int c = 0; c + 1 < NMAX; c += 2)
-            if (c < N) {
-              const unsigned long long* q = reinterpret_cast<const unsigned long long*>(&acc[c]);
-              asm volatile("st.global.v2.b64 [%0], {%1,%2};" ::"l"(pc + s_cnoff[c]), "l"(q[0]), "l"(q[1]) : "memory");
-            }
-          continue;
-        }
-      }
-      if (pair_ok) {
-#pragma unroll
-        for (int c = 0; c < NMAX; c += 2)
-          if (c < N) store_pair_of(pc + s_cnoff[c], acc[c], acc[c + 1]);
-      } else {
-#pragma unroll
-        for (int c = 0; c < NMAX; ++c)
-          if (c < N) {
-            T* p = pc + s_cnoff[c];
-            *p = accumulate ? add_of(*p, acc[c]) : acc[c];
           }
+        }
+        bool done = false;
+        if constexpr (sizeof(T) == 8) {
+          if (quad8) {
+#pragma unroll
+            for (int c = 0; c + 3 < CH; c += 4)
+              if (c0 + c < N) {
+                const unsigned long long* q = reinterpret_cast<const unsigned long long*>(&acc[c]);
+                asm volatile("st.global.v4.b64 [%0], {%1,%2,%3,%4};" ::"l"(pc + s_cnoff[c0 + c]), "l"(q[0]), "l"(q[1]),
+                             "l"(q[2]), "l"(q[3])
+                             : "memory");
+              }
+            done = true;
+          } else if (pair8) {
+#pragma unroll
+            for (int c = 0; c + 1 < CH; c += 2)
+              if (c0 + c < N) {
+                const unsigned long long* q = reinterpret_cast<const unsigned long long*>(&acc[c]);
+                asm volatile("st.global.v2.b64 [%0], {%1,%2};" ::"l"(pc + s_cnoff[c0 + c]), "l"(q[0]), "l"(q[1])
+                             : "memory");
+              }
+            done = true;
+          }
+        }
+        if (done) continue;
+        if (pair_ok) {
+#pragma unroll
+          for (int c = 0; c < CH; c += 2)
+            if (c0 + c < N) store_pair_of(pc + s_cnoff[c0 + c], acc[c], acc[c + 1]);
+        } else {
+#pragma unroll
+          for (int c = 0; c < CH; ++c)
+            if (c0 + c < N) {
+              T* p = pc + s_cnoff[c0 + c];
+              *p = accumulate ? add_of(*p, acc[c]) : acc[c];
+            }
+        }
       }
     }
   }

@@ -166,3 +166,68 @@ def test_errors_match_reference():
         L.split_equation("a...,b->")
     with pytest.raises(TypeError):
         L.dtype_name("int32")
+
+
+def test_tcgen05_descriptor_properties():
+    """Host side of the tcgen05 complex64 kernel (tc05_kernel.cuh): exact tiles, TMA run
+    flag, chunk-stride padding -- on permuted power-of-two layouts like the Sycamore nodes,
+    with the data path checked through the emulator."""
+    rng = np.random.default_rng(5)
+    seen_bulk = seen_gather = 0
+    for trial in range(40):
+        nm, nk, nn = int(rng.integers(10, 13)), int(rng.integers(4, 7)), int(rng.integers(4, 8))
+        m_ix = [chr(ord("a") + i) for i in range(nm)]
+        k_ix = [chr(ord("A") + i) for i in range(nk)]
+        n_ix = [chr(ord("n") + i) for i in range(nn)]
+        ta = list(rng.permutation(m_ix + k_ix))
+        tb = list(rng.permutation(k_ix + n_ix))
+        out = list(rng.permutation(m_ix + n_ix))
+        if trial % 5 == 4:
+            ta = ta + ["z"]  # a trailing batch index of extent 3: odd strides, no TMA runs
+            tb = tb + ["z"]
+            out = out + ["z"]
+        sizes = {c: 2 for c in m_ix + k_ix + n_ix}
+        sizes["z"] = 3
+        sa, sb = tuple(sizes[c] for c in ta), tuple(sizes[c] for c in tb)
+        dims = L.classify_pair("".join(ta), sa, "".join(tb), sb, "".join(out))
+        plan = L.build_pair_desc(dims, "complex64", sm_count=148, c_dense_elems=1, force_splitk=1)
+        W = plan.words
+        if plan.variant not in L.TC05_VARIANTS:
+            continue
+        MT, NT, KT = L.VARIANT_TILES[plan.variant]
+        assert (W[L.W_MTA], W[L.W_NTA], W[L.W_KTA]) == (MT, NT, KT)
+        run_a, pad, bulk = int(W[34]), int(W[35]), bool(W[L.W_FLAGS] & 64)
+        assert pad in (0, 1, 2, 4)
+        n_lda = int(W[L.W_NLDA])
+        lda = [tuple(int(x) for x in W[L.OFF_LDA + 4 * i:L.OFF_LDA + 4 * i + 4]) for i in range(n_lda)]
+        # the run is the dense prefix of A's load order
+        prod = 1
+        for ext, stride, _wr, _wk in lda:
+            if stride != prod:
+                break
+            prod *= ext
+        assert prod == run_a
+        if bulk:
+            seen_bulk += 1
+            assert run_a >= 16 and run_a % 2 == 0 and (MT * KT) % run_a == 0
+            assert all(s % 2 == 0 for _e, s, _r, _k in lda if s >= run_a)
+        else:
+            seen_gather += 1
+        # every (row, k) position of the tile is hit exactly once by the load order
+        pos = set()
+        for e in range(MT * KT):
+            r = kk = 0
+            x = e
+            for ext, _s, wr, wk in lda:
+                r += (x % ext) * wr
+                kk += (x % ext) * wk
+                x //= ext
+            pos.add((r, kk))
+        assert len(pos) == MT * KT and max(p[0] for p in pos) == MT - 1 and max(p[1] for p in pos) == KT - 1
+        if trial % 8 == 3:  # the data path of a few of them (emulator)
+            a, b = make_arrays([sa, sb], "complex128", seed=trial)
+            got, _ = run_pair("".join(ta) + "," + "".join(tb) + "->" + "".join(out), a.astype(np.complex64),
+                              b.astype(np.complex64), variant=plan.variant, splitk=1)
+            want = np.einsum("".join(ta) + "," + "".join(tb) + "->" + "".join(out), a, b)
+            assert rel_err(got, want) < 1e-5
+    assert seen_bulk >= 10 and seen_gather >= 3, (seen_bulk, seen_gather)
