@@ -162,6 +162,29 @@ int launch_rowstream(const int64_t* h, const int64_t* d, const void* A, const vo
   return CTGB_OK;
 }
 
+int launch_dmmastream(const int64_t* h, const int64_t* d, const void* A, const void* B, void* C, cudaStream_t st) {
+  DevInfo& di = devinfo();
+  if (!di.ok) return fail(CTGB_E_CUDA, "no CUDA device");
+  const int N = (int)h[W_NTA], K = (int)h[W_KTA];
+  if (h[W_DTYPE] != CTGB_C128 || N > 32 || K > DS_KMAX || h[W_TILES_N] != 1 || h[W_TILES_B] != 1 ||
+      h[W_STEPS_K] != 1 || h[W_SPLITK] != 1 || h[W_PGM] >= 0 && (h[W_MFULL] % h[W_MTEXT]) != 0 || h[W_PGN] >= 0 ||
+      h[W_PGK] >= 0)
+    return fail(CTGB_E_VALUE, "descriptor does not fit the DMMA stream kernel");
+  const unsigned long long M = (unsigned long long)h[W_MTA] * (unsigned long long)h[W_TILES_M];
+  if (M >= (1ull << 32)) return fail(CTGB_E_VALUE, "too many rows for the DMMA stream kernel");
+  if (M == 0) return CTGB_OK;
+  unsigned long long blocks = (M + 127) / 128;  // 4 warps x 32 rows per block and pass
+  const unsigned long long cap = (unsigned long long)di.sms * 12;
+  if (blocks > cap) blocks = cap;
+  if (N <= 16)
+    dmmastream_kernel<2><<<(unsigned)blocks, 128, 0, st>>>(d, (const double2*)A, (const double2*)B, (double2*)C);
+  else
+    dmmastream_kernel<4><<<(unsigned)blocks, 128, 0, st>>>(d, (const double2*)A, (const double2*)B, (double2*)C);
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  CUDA_TRY(cudaGetLastError());
+  return CTGB_OK;
+}
+
 // complex64 on tcgen05: prepare B' (hi/lo, tile order) once, then the warp-specialised kernel
 template <int NT>
 int launch_tc05(const int64_t* h, const int64_t* d, const void* A, const void* B, void* C, cudaStream_t st) {
@@ -238,6 +261,7 @@ template <typename T>
 int launch_gett_typed(const int64_t* h, const int64_t* d, const void* A, const void* B, void* C, cudaStream_t st) {
   const int variant = (int)h[W_VARIANT];
   if (variant == VAR_ROWSTREAM) return launch_rowstream<T>(h, d, A, B, C, st);
+  if (variant == VAR_DMMASTREAM) return launch_dmmastream(h, d, A, B, C, st);
   if constexpr (std::is_same<T, float2>::value) {
     if (variant == VAR_TC05_128x64) return launch_tc05<64>(h, d, A, B, C, st);
     if (variant == VAR_TC05_128x32) return launch_tc05<32>(h, d, A, B, C, st);

@@ -466,6 +466,7 @@ struct DmmaPolicy {
 
 #include "tf32_policy.cuh"
 #include "rowstream.cuh"
+#include "dmmastream.cuh"
 #include "tc05_policy.cuh"
 #include "gett_ws.cuh"
 #include "tc05_kernel.cuh"

@@ -59,7 +59,8 @@ SDESC_MAGIC = 0x4354474253303031
 VAR_SIMT_64x64, VAR_KRED, VAR_DMMA_128x64, VAR_DMMA_64x128, VAR_DMMA_256x32 = 0, 1, 2, 3, 4
 VAR_DMMA_256x16, VAR_ROW_128x8, VAR_ROW_256x4, VAR_ROWSTREAM = 5, 6, 7, 8
 VAR_TC05_128x64, VAR_TC05_128x32, VAR_TC05_128x16 = 9, 10, 11
-VAR_DMMA3M_128x32, VAR_DMMA3M_256x16 = 12, 13
+VAR_DMMA3M_128x32, VAR_DMMA3M_256x16, VAR_DMMASTREAM = 12, 13, 14
+DMMASTREAM_MAX_N = 16  # the kernel takes N <= 32; wider nodes are left to the staged 256x32 policy
 TC05_VARIANTS = (VAR_TC05_128x64, VAR_TC05_128x32, VAR_TC05_128x16)
 # (MT, NT, KT) of every kernel variant -- must match ctg_b200.cu's dispatch
 VARIANT_TILES = {
@@ -77,6 +78,7 @@ VARIANT_TILES = {
     VAR_TC05_128x16: (128, 16, 16),
     VAR_DMMA3M_128x32: (128, 32, 16),
     VAR_DMMA3M_256x16: (256, 16, 8),
+    VAR_DMMASTREAM: (256, 32, 32),
 }
 
 DTYPE_CODES = {"float32": 0, "float64": 1, "complex64": 2, "complex128": 3}
@@ -330,6 +332,10 @@ def choose_variant(dtype, B, M, N, K, allow_dmma=True, allow_stream=True, allow_
         return VAR_ROWSTREAM
     if N <= 8 and M >= 64:
         return VAR_ROW_256x4 if N <= 4 else VAR_ROW_128x8
+    # narrow complex128 nodes: DMMA fragments streamed from global memory, no staging
+    if (allow_dmma and allow_stream and dtype == "complex128" and N <= DMMASTREAM_MAX_N and K <= 32 and B == 1
+            and 4096 <= M < 1 << 32):
+        return VAR_DMMASTREAM
     # complex64 dense nodes with exact power-of-two tiles: tcgen05 (kind::tf32 x3, TMEM)
     if (allow_dmma and allow_tc05 and dtype == "complex64" and M % 128 == 0 and K % 16 == 0
             and K <= 256 and M * N * K >= 1 << 20):
@@ -381,6 +387,8 @@ def build_pair_desc(dims: PairDims, dtype, accumulate=False, sm_count=148,
     if variant in (VAR_DMMA3M_128x32, VAR_DMMA3M_256x16) and dtype != "complex128":
         # the 3M identity is a complex128 kernel: other dtypes take the plain tensor-core tiles
         variant = VAR_DMMA_256x32 if variant == VAR_DMMA3M_128x32 else VAR_DMMA_256x16
+    if variant == VAR_DMMASTREAM and not (dtype == "complex128" and N <= 32 and K <= 32 and B == 1 and M < 1 << 32):
+        variant = VAR_DMMA_256x16
     if variant == VAR_ROWSTREAM:
         # the streaming kernel needs exact tiles: every m dim must divide
         ok = N <= 8 and K <= 8 and B == 1 and M < 1 << 32 and all(
@@ -490,6 +498,9 @@ def build_pair_desc(dims: PairDims, dtype, accumulate=False, sm_count=148,
             return build_pair_desc(dims, dtype, accumulate=accumulate, sm_count=sm_count, variant=fb,
                                    allow_dmma=allow_dmma, c_dense_elems=c_dense_elems,
                                    force_splitk=force_splitk)
+    if variant == VAR_DMMASTREAM and (pn is not None or pk is not None or (pm is not None and pm[1] % pm[2] != 0)):
+        return build_pair_desc(dims, dtype, accumulate=accumulate, sm_count=sm_count, variant=VAR_DMMA_256x16,
+                               allow_dmma=allow_dmma, c_dense_elems=c_dense_elems, force_splitk=force_splitk)
     if variant == VAR_ROWSTREAM and pm is not None and pm[1] % pm[2] != 0:
         # ragged blocked m dim: fall back to the staged row policy
         return build_pair_desc(dims, dtype, accumulate=accumulate, sm_count=sm_count,

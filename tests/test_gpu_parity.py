@@ -106,7 +106,7 @@ def test_tensordot_golden_shapes():
 
 @pytest.mark.parametrize("variant", [L.VAR_SIMT_64x64, L.VAR_DMMA_128x64, L.VAR_DMMA_64x128,
                                      L.VAR_DMMA_256x32, L.VAR_DMMA_256x16, L.VAR_ROW_128x8, L.VAR_ROW_256x4, L.VAR_ROWSTREAM, L.VAR_TC05_128x64, L.VAR_TC05_128x32, L.VAR_TC05_128x16,
-                                     L.VAR_DMMA3M_128x32, L.VAR_DMMA3M_256x16])
+                                     L.VAR_DMMA3M_128x32, L.VAR_DMMA3M_256x16, L.VAR_DMMASTREAM])
 @pytest.mark.parametrize("dtype", ["complex128", "float64", "complex64", "float32"])
 def test_every_kernel_variant_ragged_gemm(variant, dtype):
     import torch
@@ -189,6 +189,44 @@ def test_tcgen05_kernel_modes(case, misalign):
         want = want + c0
     assert rel_err(dc.cpu().numpy().reshape(out_shape), want) < 1e-5, name
     del keep_a, keep_b
+
+
+DSTREAM_CASES = [
+    ("n16_k16", "ab,bc->ac", [(8192, 16), (16, 16)], {}),
+    ("ragged_rows_cols", "xyzb,bc->zyxc", [(8, 27, 19, 7), (7, 11)], {}),   # 4104 rows (masked tail), odd N, K % 4 != 0
+    ("n32_k32", "ab,bc->ac", [(4096, 32), (32, 32)], {}),                 # four column fragments
+    ("n24_k20", "bxy,cb->cyx", [(20, 72, 72), (24, 20)], {}),              # transposed operands and output
+    ("permuted", "aibjc,ijd->dcba", [(8, 4, 8, 4, 8), (4, 4, 16)], {}),   # multi-dim rows, strided C
+    ("accumulate", "ab,bc->ac", [(4096, 16), (16, 16)], {"accumulate": True}),
+]
+
+
+@pytest.mark.parametrize("case", DSTREAM_CASES, ids=[c[0] for c in DSTREAM_CASES])
+def test_dmma_stream_kernel(case):
+    """dmmastream.cuh: DMMA fragments loaded straight from global memory (narrow complex128 nodes)."""
+    import torch
+
+    from cotengra_b200 import _lib
+
+    name, eq, shapes, kw = case
+    lhs, out = eq.split("->")
+    ta_, tb_ = lhs.split(",")
+    a, b = make_arrays(shapes, "complex128", seed=len(name))
+    dims = L.classify_pair(ta_, a.shape, tb_, b.shape, out)
+    out_shape = tuple(dict(zip(ta_ + tb_, a.shape + b.shape))[ix] for ix in out)
+    plan = L.build_pair_desc(dims, "complex128", c_dense_elems=math.prod(out_shape), variant=L.VAR_DMMASTREAM,
+                             sm_count=_lib.device_info()["sm_count"], **kw)
+    assert plan.variant == L.VAR_DMMASTREAM, (name, plan.variant)
+    da, db = torch.from_numpy(np.ascontiguousarray(a)).cuda(), torch.from_numpy(np.ascontiguousarray(b)).cuda()
+    c0 = make_arrays([out_shape], "complex128", seed=78)[0]
+    dc = torch.from_numpy(np.ascontiguousarray(c0)).cuda()
+    pa, pb = (db, da) if plan.swapped else (da, db)
+    _lib.check(_lib.load().ctgb_contract_pair(plan.words.ctypes.data, pa.data_ptr(), pb.data_ptr(), dc.data_ptr(), 0))
+    torch.cuda.synchronize()
+    want = np.einsum(eq, a, b)
+    if kw.get("accumulate"):
+        want = want + c0
+    assert rel_err(dc.cpu().numpy().reshape(out_shape), want) < 1e-12, name
 
 
 def test_equations_through_contractor():
