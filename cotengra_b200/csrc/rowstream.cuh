@@ -95,7 +95,7 @@ rowstream_kernel(const int64_t* __restrict__ D, const T* __restrict__ A, const T
   const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
   // rows per thread and iteration: narrow element types need more loads in flight
   // per thread to cover HBM latency (Little's law at <= 24 resident warps / SM)
-  constexpr int R = sizeof(T) >= 16 ? 1 : 2;
+  constexpr int R = sizeof(T) >= 16 ? 1 : ((sizeof(T) == 8 && KMAX <= 4) ? 4 : 2);
   for (unsigned long long m0 = (unsigned long long)blockIdx.x * blockDim.x + tid; m0 < M; m0 += stride * R) {
     long long oa[R], oc[R];
     bool live[R];
