@@ -162,6 +162,25 @@ int launch_rowstream(const int64_t* h, const int64_t* d, const void* A, const vo
   return CTGB_OK;
 }
 
+template <typename T>
+int launch_dotstream(const int64_t* h, const int64_t* d, const void* A, const void* B, void* C, cudaStream_t st) {
+  DevInfo& di = devinfo();
+  if (!di.ok) return fail(CTGB_E_CUDA, "no CUDA device");
+  if (h[W_MTA] != 1 || h[W_NTA] != 1 || h[W_TILES_M] != 1 || h[W_TILES_N] != 1 || h[W_TILES_B] != 1 ||
+      h[W_KTA] > DOT_KT || h[W_NGK] > 64 || h[W_STEPS_K] >= (1ll << 31) ||
+      (h[W_PGK] >= 0 && (h[W_KFULL] % h[W_KTEXT]) != 0))
+    return fail(CTGB_E_VALUE, "descriptor does not fit the dot-stream kernel");
+  if (h[W_STEPS_K] == 0) return CTGB_OK;
+  if (!(h[W_FLAGS] & 1)) CUDA_TRY(cudaMemsetAsync(C, 0, sizeof(T), st));
+  unsigned long long blocks = (unsigned long long)h[W_STEPS_K];
+  const unsigned long long cap = (unsigned long long)di.sms * 2;  // two resident blocks per SM, one wave
+  if (blocks > cap) blocks = cap;
+  dotstream_kernel<T><<<(unsigned)blocks, DOT_THREADS, 0, st>>>(d, (const T*)A, (const T*)B, (T*)C);
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  CUDA_TRY(cudaGetLastError());
+  return CTGB_OK;
+}
+
 int launch_dmmastream(const int64_t* h, const int64_t* d, const void* A, const void* B, void* C, cudaStream_t st) {
   DevInfo& di = devinfo();
   if (!di.ok) return fail(CTGB_E_CUDA, "no CUDA device");
@@ -262,6 +281,7 @@ int launch_gett_typed(const int64_t* h, const int64_t* d, const void* A, const v
   const int variant = (int)h[W_VARIANT];
   if (variant == VAR_ROWSTREAM) return launch_rowstream<T>(h, d, A, B, C, st);
   if (variant == VAR_DMMASTREAM) return launch_dmmastream(h, d, A, B, C, st);
+  if (variant == VAR_DOTSTREAM) return launch_dotstream<T>(h, d, A, B, C, st);
   if constexpr (std::is_same<T, float2>::value) {
     if (variant == VAR_TC05_128x64) return launch_tc05<64>(h, d, A, B, C, st);
     if (variant == VAR_TC05_128x32) return launch_tc05<32>(h, d, A, B, C, st);

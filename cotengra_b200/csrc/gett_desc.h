@@ -74,6 +74,7 @@ enum : int {
   VAR_TC05_128x16 = 11,
   VAR_DMMA3M_128x32 = 12,  // complex128, 3M complex product (three DMMAs per fragment pair)
   VAR_DMMA3M_256x16 = 13,
+  VAR_DOTSTREAM = 15,      // M = N = 1: the final inner product, operands straight from global memory
   VAR_DMMASTREAM = 14      // complex128, 8 < N <= 16, K <= 32: DMMA fragments straight from global memory
 };
 

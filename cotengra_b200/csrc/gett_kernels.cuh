@@ -467,6 +467,7 @@ struct DmmaPolicy {
 #include "tf32_policy.cuh"
 #include "rowstream.cuh"
 #include "dmmastream.cuh"
+#include "dotstream.cuh"
 #include "tc05_policy.cuh"
 #include "gett_ws.cuh"
 #include "tc05_kernel.cuh"

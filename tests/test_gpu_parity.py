@@ -106,7 +106,7 @@ def test_tensordot_golden_shapes():
 
 @pytest.mark.parametrize("variant", [L.VAR_SIMT_64x64, L.VAR_DMMA_128x64, L.VAR_DMMA_64x128,
                                      L.VAR_DMMA_256x32, L.VAR_DMMA_256x16, L.VAR_ROW_128x8, L.VAR_ROW_256x4, L.VAR_ROWSTREAM, L.VAR_TC05_128x64, L.VAR_TC05_128x32, L.VAR_TC05_128x16,
-                                     L.VAR_DMMA3M_128x32, L.VAR_DMMA3M_256x16, L.VAR_DMMASTREAM])
+                                     L.VAR_DMMA3M_128x32, L.VAR_DMMA3M_256x16, L.VAR_DMMASTREAM, L.VAR_DOTSTREAM])
 @pytest.mark.parametrize("dtype", ["complex128", "float64", "complex64", "float32"])
 def test_every_kernel_variant_ragged_gemm(variant, dtype):
     import torch
@@ -227,6 +227,41 @@ def test_dmma_stream_kernel(case):
     if kw.get("accumulate"):
         want = want + c0
     assert rel_err(dc.cpu().numpy().reshape(out_shape), want) < 1e-12, name
+
+
+@pytest.mark.parametrize("dtype", ["complex128", "complex64", "float64", "float32"])
+@pytest.mark.parametrize("case", ["pow2_permuted", "odd_extents", "accumulate"])
+def test_dot_stream_kernel(case, dtype):
+    """dotstream.cuh: M = N = 1 inner products with differently ordered operands."""
+    import torch
+
+    from cotengra_b200 import _lib
+
+    if case == "odd_extents":
+        ta_, tb_, shape = "abcd", "dbca", {"a": 32, "b": 27, "c": 25, "d": 49}
+    else:
+        ta_ = "abcdefghijklmnopqrstu"
+        tb_ = "utsrqpjihgfedcbaonmlk"
+        shape = {c: 2 for c in ta_}
+    sa, sb = tuple(shape[c] for c in ta_), tuple(shape[c] for c in tb_)
+    a, b = make_arrays([sa, sb], dtype, seed=11)
+    dims = L.classify_pair(ta_, sa, tb_, sb, "")
+    acc = case == "accumulate"
+    plan = L.build_pair_desc(dims, dtype, c_dense_elems=1, accumulate=acc, sm_count=_lib.device_info()["sm_count"])
+    assert plan.variant == L.VAR_DOTSTREAM, plan.variant
+    da, db = torch.from_numpy(a).cuda(), torch.from_numpy(b).cuda()
+    c0 = make_arrays([(1,)], dtype, seed=3)[0]
+    dc = torch.from_numpy(c0.copy()).cuda()
+    pa, pb = (db, da) if plan.swapped else (da, db)
+    _lib.check(_lib.load().ctgb_contract_pair(plan.words.ctypes.data, pa.data_ptr(), pb.data_ptr(), dc.data_ptr(), 0))
+    torch.cuda.synchronize()
+    wide = np.complex128 if np.dtype(dtype).kind == "c" else np.float64
+    want = np.einsum(ta_ + "," + tb_ + "->", a.astype(wide), b.astype(wide))
+    scale = np.sqrt(a.size)  # sum of ~N(0,1) terms: compare against the natural magnitude
+    if acc:
+        want = want + c0[0]
+    tol = 1e-12 if dtype in ("complex128", "float64") else 2e-5
+    assert abs(dc.cpu().numpy()[0] - want) / scale < tol, (case, dtype)
 
 
 def test_equations_through_contractor():

@@ -13,7 +13,7 @@ PARSERS = load_json("parsers.json")
 PVALS = load_npz("parsers_values.npz")
 VARIANTS = [L.VAR_SIMT_64x64, L.VAR_DMMA_128x64, L.VAR_DMMA_64x128, L.VAR_DMMA_256x32,
             L.VAR_DMMA_256x16, L.VAR_ROW_128x8, L.VAR_ROW_256x4, L.VAR_ROWSTREAM, L.VAR_TC05_128x64, L.VAR_TC05_128x32, L.VAR_TC05_128x16,
-            L.VAR_DMMA3M_128x32, L.VAR_DMMA3M_256x16, L.VAR_DMMASTREAM]
+            L.VAR_DMMA3M_128x32, L.VAR_DMMA3M_256x16, L.VAR_DMMASTREAM, L.VAR_DOTSTREAM]
 
 
 def run_pair(eq, a, b, variant=None, splitk=None, sm_count=148):
