@@ -3,8 +3,8 @@
 // after gett_ws.cuh (mbarrier helpers) and tc05_policy.cuh (bprime_kernel, descriptors).
 //
 // A complex tile product C[128 x NT] += A[128 x 16] * B[16 x NT] runs as the real
-// product C'[128 x 2NT] += A'[128 x 32] * B'[2NT x 32]^T (tc05_policy.cuh), three times
-// for the 3xTF32 split.  The CTA is specialised into four roles that only meet at
+// product C'[128 x 2NT] += A'[128 x 32] * B'[2NT x 32]^T (tc05_policy.cuh); the 3xTF32 split
+// (hi*hi + lo*hi + hi*lo) takes two UMMAs per k8 because B'hi and B'lo are stacked along N.  The CTA is specialised into four roles that only meet at
 // mbarriers:
 //
 //   warps  8-11  A producers   the A tile of a k-step is fetched in A's MEMORY order
@@ -20,7 +20,7 @@
 //                              layout (double buffered A' images).
 //   warp   13    MMA issuer    a whole warp runs the issue loop with warp-uniform control
 //                              flow (descriptors stay in uniform registers); one elected
-//                              lane issues the 12 UMMAs of a k-step and commits them to the
+//                              lane issues the 8 UMMAs of a k-step and commits them to the
 //                              "operand free", "B' slot free" and (last step) "accumulator
 //                              full" barriers.  Kept apart from the scatter warps: the
 //                              issue sequence costs ~1300 clk per step when it runs
@@ -38,16 +38,16 @@ template <int NT_>
 struct Tc05Cfg {
   static constexpr int MT = 128, NT = NT_, KT = 16;
   static constexpr int SA_MAX = 8, NB_MAX = 8;             // ring depths are chosen per launch
-  static constexpr int TILE_FLOATS = 8 * (2 * NT) * 4;     // one B' tile: [8 chunks][2NT rows][4 floats]
-  static constexpr int PAIR_BYTES = 2 * TILE_FLOATS * 4;   // hi + lo
+  static constexpr int TILE_FLOATS = 8 * (2 * NT) * 4;     // floats of B'hi (or B'lo) of one k-step
+  static constexpr int PAIR_BYTES = 2 * TILE_FLOATS * 4;   // [8 chunks][4NT rows: 2NT hi, then 2NT lo][4 floats]
   static constexpr int A_TILE = MT * KT;                   // float2 elements of one staged A tile
   static constexpr int LBO_BASE = MT * 16;                 // bytes between k chunks of A' (unpadded)
   static constexpr int OP_BYTES = 8 * (LBO_BASE + 64);     // one A' image with the largest padding
-  static constexpr int TMEM_COLS = 2 * NT;                 // fp32 columns of one accumulator
+  static constexpr int TMEM_COLS = 4 * NT;                 // fp32 columns of one accumulator: [A'hi B'hi + A'lo B'hi | A'hi B'lo]
   static constexpr int TI = SA_MAX + 4;                    // tile-info ring (epilogue lags <= 2 tiles)
   static constexpr int NBARS = 2 * SA_MAX + 2 * NB_MAX + 2 + 2 + 4;
   static constexpr int THREADS = 14 * 32;
-  static_assert(TMEM_COLS == 32 || TMEM_COLS == 64 || TMEM_COLS == 128,
+  static_assert(TMEM_COLS == 64 || TMEM_COLS == 128 || TMEM_COLS == 256,
                 "two accumulators: a power of two >= 32 columns each, <= 512 together");
   static constexpr size_t fixed_bytes() {  // everything but the two rings
     return 4 * (size_t)OP_BYTES + 8 * (size_t)(MT + NT + KCHUNK + 4 * TI + NBARS) + 128;
@@ -374,8 +374,14 @@ tc05_kernel(const int64_t* __restrict__ D, const float2* __restrict__ A, const f
   } else if (warp == 13) {
     // ===================================================== MMA ISSUER (warp-uniform loop)
     // InstrDescriptor: D=f32 [4,6)=1, A=tf32 [7,10)=2, B=tf32 [10,13)=2, K-major A/B, N>>3 [17,23), M>>4 [24,29)
-    constexpr unsigned idesc =
-        (1u << 4) | (2u << 7) | (2u << 10) | ((unsigned)(Cfg::TMEM_COLS >> 3) << 17) | ((unsigned)(MT >> 4) << 24);
+    // Two instructions per k8 instead of three passes: B'hi and B'lo are stacked along N, so
+    //   [P | Q] (4NT columns)  = A'hi x [B'hi ; B'lo]^T      (A'hi is read from shared memory once)
+    //    P      (2NT columns) += A'lo x  B'hi^T
+    // and the epilogue adds the small term Q to P.
+    constexpr unsigned idesc_wide =
+        (1u << 4) | (2u << 7) | (2u << 10) | ((unsigned)((4 * NT) >> 3) << 17) | ((unsigned)(MT >> 4) << 24);
+    constexpr unsigned idesc_half =
+        (1u << 4) | (2u << 7) | (2u << 10) | ((unsigned)((2 * NT) >> 3) << 17) | ((unsigned)(MT >> 4) << 24);
     const unsigned op_base = (unsigned)__cvta_generic_to_shared(op);
     const unsigned b_base = (unsigned)__cvta_generic_to_shared(sB);
     unsigned g = 0;
@@ -395,24 +401,26 @@ tc05_kernel(const int64_t* __restrict__ D, const float2* __restrict__ A, const f
         }
         asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
         const unsigned a_hi = op_base + (ob * 2) * (unsigned)Cfg::OP_BYTES, a_lo = a_hi + (unsigned)Cfg::OP_BYTES;
-        const unsigned b_hi = b_base + sb * (unsigned)Cfg::PAIR_BYTES, b_lo = b_hi + Cfg::TILE_FLOATS * 4;
+        const unsigned b_all = b_base + sb * (unsigned)Cfg::PAIR_BYTES;
         const unsigned dcol = taddr + buf * Cfg::TMEM_COLS;
         if (elect_one()) {
 #pragma unroll
-          for (int pass = 0; pass < 3; ++pass) {
-            const unsigned a0 = pass == 0 ? a_lo : a_hi, b0 = pass == 1 ? b_lo : b_hi;  // lo*hi, hi*lo, hi*hi
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {
-              // one UMMA eats K = 8 floats = 2 chunks; chunk stride = LBO, 8-row group stride (SBO) = 128 B
-              const uint64_t da = umma_desc_kmajor(a0 + q * 2 * lbo_a, lbo_a, 128);
-              const uint64_t db = umma_desc_kmajor(b0 + q * 2 * (2 * NT) * 16, (2 * NT) * 16, 128);
-              const unsigned acc = (step != k0 || pass != 0 || q != 0) ? 1u : 0u;
-              asm volatile(
-                  "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-                  "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(dcol),
-                  "l"(da), "l"(db), "r"(idesc), "r"(acc)
-                  : "memory");
-            }
+          for (int q = 0; q < 4; ++q) {
+            // one UMMA eats K = 8 floats = 2 chunks; chunk stride = LBO, 8-row group stride (SBO) = 128 B
+            const uint64_t d_hi = umma_desc_kmajor(a_hi + q * 2 * lbo_a, lbo_a, 128);
+            const uint64_t d_lo = umma_desc_kmajor(a_lo + q * 2 * lbo_a, lbo_a, 128);
+            const uint64_t d_b = umma_desc_kmajor(b_all + q * 2 * (4 * NT) * 16, (4 * NT) * 16, 128);
+            const unsigned acc = (step != k0 || q != 0) ? 1u : 0u;
+            asm volatile(
+                "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(dcol),
+                "l"(d_hi), "l"(d_b), "r"(idesc_wide), "r"(acc)
+                : "memory");
+            asm volatile(
+                "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(dcol),
+                "l"(d_lo), "l"(d_b), "r"(idesc_half), "r"(1u)
+                : "memory");
           }
           const unsigned m_op = (unsigned)__cvta_generic_to_shared(&op_empty[ob]);
           asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n" ::"r"(m_op)
@@ -456,7 +464,19 @@ tc05_kernel(const int64_t* __restrict__ D, const float2* __restrict__ A, const f
               "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
               "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
             : "r"(ta));
+        // the small term A'hi B'lo sits 2NT columns further
+        unsigned u[32];
+        asm volatile(
+            "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,"
+            "%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];\n"
+            : "=r"(u[0]), "=r"(u[1]), "=r"(u[2]), "=r"(u[3]), "=r"(u[4]), "=r"(u[5]), "=r"(u[6]), "=r"(u[7]), "=r"(u[8]),
+              "=r"(u[9]), "=r"(u[10]), "=r"(u[11]), "=r"(u[12]), "=r"(u[13]), "=r"(u[14]), "=r"(u[15]), "=r"(u[16]),
+              "=r"(u[17]), "=r"(u[18]), "=r"(u[19]), "=r"(u[20]), "=r"(u[21]), "=r"(u[22]), "=r"(u[23]), "=r"(u[24]),
+              "=r"(u[25]), "=r"(u[26]), "=r"(u[27]), "=r"(u[28]), "=r"(u[29]), "=r"(u[30]), "=r"(u[31])
+            : "r"(ta + 2u * NT));
         asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
+#pragma unroll
+        for (int i = 0; i < 32; ++i) v[i] = __float_as_uint(__uint_as_float(v[i]) + __uint_as_float(u[i]));
 #pragma unroll
         for (int s4 = 0; s4 < 4; ++s4) {  // groups of 4 complex columns
           const int c0 = (col >> 1) + s4 * 4;

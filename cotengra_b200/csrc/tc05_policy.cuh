@@ -6,7 +6,7 @@
 // (re, im)-interleaved image and B' is the 2x2-block embedding
 //   B'[2n][2k] = Br   B'[2n][2k+1] = -Bi   B'[2n+1][2k] = Bi   B'[2n+1][2k+1] = Br
 // so that C' is C's own interleaved image.  fp32 accuracy comes from the 3xTF32
-// split  D += A'lo*B'hi + A'hi*B'lo + A'hi*B'hi  (the tensor core truncates its
+// split  D = (A'hi*B'hi + A'lo*B'hi) + A'hi*B'lo  (the tensor core truncates its
 // operands to tf32, so "hi" is the raw fp32 word and lo = x - trunc_tf32(x)):
 // 1.3e-6 relative on a K = 64 tile (scripts/ubench/umma_c64.cu).
 //
@@ -25,7 +25,7 @@ __device__ __forceinline__ uint64_t umma_desc_kmajor(uint32_t saddr, uint32_t lb
 __device__ __forceinline__ float trunc_tf32(float x) { return __uint_as_float(__float_as_uint(x) & 0xFFFFE000u); }
 
 // B -> B'hi / B'lo in shared-memory tile order:
-//   Bp[((ib*tiles_n + in)*steps_k + step)][hi|lo][chunk 0..7][row 0..2NT-1][4 floats]
+//   Bp[((ib*tiles_n + in)*steps_k + step)][chunk 0..7][row 0..4NT-1: hi rows, then lo rows][4 floats]
 template <int NT>
 __global__ void __launch_bounds__(256) bprime_kernel(const int64_t* __restrict__ D, const float2* __restrict__ B,
                                                      float* __restrict__ Bp) {
@@ -71,8 +71,10 @@ __global__ void __launch_bounds__(256) bprime_kernel(const int64_t* __restrict__
     }
     const float2 b = B[off];
     const float v = (q == p) ? b.x : (q == 0 ? -b.y : b.y);
-    const unsigned long long base = (idx / TILE) * (2ull * TILE);
-    Bp[base + e] = v;                        // hi: raw fp32 (the tensor core truncates)
-    Bp[base + TILE + e] = v - trunc_tf32(v); // lo
+    // stacked along N: chunk c holds 4NT rows -- rows [0, 2NT) are B'hi, rows [2NT, 4NT) are B'lo --
+    // so that one UMMA of N = 4NT multiplies A'hi with both and one of N = 2NT takes B'hi alone
+    const unsigned long long base = (idx / TILE) * (2ull * TILE) + ((unsigned long long)chunk * (4 * NT)) * 4 + j;
+    Bp[base + row * 4] = v;                                 // hi: raw fp32 (the tensor core truncates)
+    Bp[base + (row + 2 * NT) * 4] = v - trunc_tf32(v);      // lo
   }
 }
