@@ -441,16 +441,21 @@ def contract_distributed(tree, arrays, root=None, group=None, strip_exponent=Fal
     over ``torch.distributed`` (NCCL on NVLink): rank ``r`` of ``W`` contracts
     slices ``r, r+W, ...`` (core.py:4070), sums them locally on its GPU, then a
     single all-reduce (``root=None``) or reduce (``root=int``) combines the
-    partial results.  Refuses sliced output indices and fewer slices than ranks
-    exactly as the reference does (core.py:4051-4066)."""
+    partial results.  Refuses fewer slices than ranks as the reference does
+    (core.py:4062-4066).  Sliced *output* indices, which ``contract_mpi`` refuses
+    (core.py:4051-4055), are sharded too: every rank scatters its
+    slices into the chunks of a zeroed full-size output (the executor's root
+    strides, core.py:3865-3876), so the same single all-reduce assembles the
+    stacked result; only the combination with ``strip_exponent`` stays refused."""
     import torch.distributed as dist
 
     torch = _torch()
     spec = executor.spec if executor is not None else (
         tree if isinstance(tree, TreeSpec) else TreeSpec.from_cotengra(tree))
-    if not {s[0] for s in spec.sliced}.isdisjoint(spec.output):
+    strip = executor.strip_exponent if executor is not None else strip_exponent
+    if strip and not {s[0] for s in spec.sliced}.isdisjoint(spec.output):
         raise NotImplementedError(
-            "Sliced and output indices overlap - currently only a simple "
+            "Sliced and output indices overlap - with stripped exponents only a simple "
             "sum of result slices is supported currently."
         )
     rank, world = dist.get_rank(group), dist.get_world_size(group)

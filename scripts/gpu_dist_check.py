@@ -37,6 +37,30 @@ for name in ("lattice6x6_d3_sliced", "lattice4x4_sliced"):
     if rank == 0:
         print(f"{name}: world={world} allreduce={e1:.1e} stripped={e2:.1e} reduce_root={e3:.1e}")
     ok = ok and max(e1, e2, e3) < 1e-10
+# sliced OUTPUT indices sharded over the ranks (beyond contract_mpi, which refuses them):
+# every rank scatters its slices into a zeroed full-size output, one all-reduce assembles it
+for name in ("rand_r3_o1_hi0_ho1_None_s42_sliced_out", "rand_r2_o1_hi1_ho2_root_s42_sliced_out",
+             "rand_r3_o2_hi0_ho1_None_s7_sliced_out"):
+    rec = next(r for r in load_json("trees.json") if r["name"] == name)
+    n_in = len(rec["inputs"])
+    node_inds = {int(k): v for k, v in rec["inds"].items() if int(k) >= n_in}
+    spec = cb.TreeSpec(rec["inputs"], rec["output"], rec["size_dict"], rec["path"],
+                       decode_sliced(rec["sliced"]), node_inds)
+    arrays = make_arrays(spec.shapes(), rec["dtype"], seed=rec["seed"])
+    want = vals[name]
+    got = cb.contract_distributed(spec, arrays)
+    e1 = rel_err(got, want)
+    r0 = cb.contract_distributed(spec, arrays, root=world - 1)
+    e2 = rel_err(r0, want) if rank == world - 1 else (0.0 if r0 is None else 1.0)
+    try:
+        cb.contract_distributed(spec, arrays, strip_exponent=True)
+        e3 = 1.0
+    except NotImplementedError:
+        e3 = 0.0
+    if rank == 0:
+        print(f"{name}: world={world} nslices={spec.nslices} sliced-output allreduce={e1:.1e} "
+              f"reduce_root={e2:.1e} stripped_refused={e3 == 0.0}")
+    ok = ok and max(e1, e2, e3) < 1e-10
 t = torch.tensor([1 if ok else 0], device="cuda")
 dist.all_reduce(t, op=dist.ReduceOp.MIN)
 if rank == 0:
