@@ -285,6 +285,74 @@ def contract_tree(tree, arrays, strip_exponent=False, check_zero=False, dtype=No
     return res
 
 
+def _combine_stripped(m1, e1, m2, e2):
+    """``AdderWithMaybeExponentStripped`` (cotengra/core.py:163-170) for two
+    (mantissa, exponent) partial sums."""
+    if e1 == -math.inf:
+        return m2, e2
+    if e2 == -math.inf:
+        return m1, e1
+    e = max(e1, e2)
+    return m1 * 10.0 ** (e1 - e) + m2 * 10.0 ** (e2 - e), e
+
+
+def contract_checkpointed(tree, arrays, checkpoint, every=1024, strip_exponent=False, dtype=None,
+                          executor=None, on_block=None, **plan_opts):
+    """``tree.contract(arrays)`` for runs too long to lose (partial-sum
+    checkpointing; the reference has no equivalent -- ``tree.contract`` restarts at
+    slice 0): the slices are contracted in blocks of ``every``, and after each block
+    the running sum -- ``(mantissa, exponent)`` with ``strip_exponent``, combined as
+    core.py:163-170 -- and the next slice id are written to ``checkpoint`` (.npz,
+    atomic replace).  A later call with the same tree, dtype and input values finds
+    the file and resumes behind the last completed block; a file written for a
+    different tree or different inputs is refused (``ValueError``), never silently
+    overwritten.  Slices are independent, so the result equals the uninterrupted
+    run up to floating-point summation order.  numpy inputs and outputs (host path).
+    ``on_block(next_slice, nslices)`` is called after every saved block."""
+    import hashlib
+    import os
+
+    if executor is None:
+        if dtype is None:
+            dtype = dtype_name(arrays[0].dtype)
+        executor = TreeExecutor(tree, dtype=dtype, strip_exponent=strip_exponent, **plan_opts)
+    ex = executor
+    spec = ex.spec
+    host = [np.asarray(a, dtype=ex.dtype, order="C") for a in arrays]
+    h = hashlib.sha256()
+    h.update(spec.to_json().encode())
+    h.update(f"|{ex.dtype}|{int(bool(ex.strip_exponent))}|".encode())
+    for a in host:
+        h.update(str(a.shape).encode())
+        h.update(a.tobytes())
+    tag = h.hexdigest()
+    nslices = int(ex.nslices)
+    every = max(1, int(every))
+
+    done, total, exponent = 0, None, -math.inf
+    if os.path.exists(checkpoint):
+        with np.load(checkpoint, allow_pickle=False) as z:
+            if str(z["tag"]) != tag:
+                raise ValueError(f"{checkpoint} belongs to a different tree, dtype or set of input values")
+            done, total, exponent = int(z["next_slice"]), z["partial"], float(z["exponent"])
+    while done < nslices:
+        count = min(every, nslices - done)
+        res = ex.contract_host(host, done, 1, count)
+        if ex.strip_exponent:
+            m, e = res
+            total, exponent = (m, float(e)) if total is None else _combine_stripped(total, exponent, m, float(e))
+        else:
+            total = res if total is None else total + res
+        done += count
+        tmp = f"{checkpoint}.tmp.npz"
+        np.savez(tmp, tag=np.array(tag), next_slice=np.int64(done), partial=np.asarray(total),
+                 exponent=np.float64(exponent))
+        os.replace(tmp, checkpoint)
+        if on_block is not None:
+            on_block(done, nslices)
+    return (total, exponent) if ex.strip_exponent else total
+
+
 def _finish_stripped(m, e, check_zero):
     if check_zero and e == -math.inf:
         # contract.py:819-820

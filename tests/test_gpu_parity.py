@@ -321,6 +321,35 @@ def test_trees_golden(rec):
     assert rel_err(got32, want) < 2e-4  # long fp32 chains; per-node bound is 1e-5
 
 
+@pytest.mark.parametrize("strip", [False, True])
+def test_checkpointed_run_resumes(strip, tmp_path):
+    """contract_checkpointed on the real executor: an interrupted run resumes
+    behind its last saved block and ends at the golden value of the reference."""
+    rec = next(r for r in TREES if r["name"] == "lattice6x6_d3_sliced")
+    n_in = len(rec["inputs"])
+    node_inds = {int(k): v for k, v in rec["inds"].items() if int(k) >= n_in}
+    spec = cb.TreeSpec(rec["inputs"], rec["output"], rec["size_dict"], rec["path"], decode_sliced(rec["sliced"]),
+                       node_inds)
+    arrays = make_arrays(spec.shapes(), rec["dtype"], seed=rec["seed"])
+    ck = str(tmp_path / "ck.npz")
+    every = max(1, spec.nslices // 4)
+
+    class Stop(Exception):
+        pass
+
+    def stop(done, n):
+        raise Stop
+
+    with pytest.raises(Stop):
+        cb.contract_checkpointed(spec, arrays, ck, every=every, strip_exponent=strip, on_block=stop)
+    blocks = []
+    res = cb.contract_checkpointed(spec, arrays, ck, every=every, strip_exponent=strip,
+                                   on_block=lambda d, n: blocks.append(d))
+    assert blocks[0] == 2 * every and blocks[-1] == spec.nslices
+    got = res[0] * 10.0 ** res[1] if strip else res
+    assert rel_err(got, TVALS[rec["name"]]) < 1e-10
+
+
 def test_contractor_dropin_signature():
     rec = next(r for r in TREES if r["name"] == "lattice4x4_sliced")
     spec = _spec(rec)
