@@ -22,6 +22,7 @@ from .executor import ExecPlan
 from .contract import (
     B200Contractor,
     TreeExecutor,
+    benchmark,
     contract_checkpointed,
     contract_distributed,
     contract_tree,
@@ -37,6 +38,6 @@ from .contract import (
 __all__ = [
     "TreeSpec", "get_symbol", "PairDims", "build_pair_desc", "build_single_desc",
     "classify_pair", "classify_single", "ExecPlan", "B200Contractor", "TreeExecutor",
-    "contract_checkpointed", "contract_distributed", "contract_tree", "einsum", "implementation", "install",
+    "benchmark", "contract_checkpointed", "contract_distributed", "contract_tree", "einsum", "implementation", "install",
     "make_contractor", "rank_slices", "reduce_partials", "tensordot",
 ]

@@ -285,6 +285,56 @@ def contract_tree(tree, arrays, strip_exponent=False, check_zero=False, dtype=No
     return res
 
 
+def benchmark(tree, dtype="float64", max_time=60, min_reps=3, max_reps=100, warmup=True,
+              executor=None, **plan_opts):
+    """``tree.benchmark(dtype, max_time, min_reps, max_reps, warmup)`` (cotengra/core.py:
+    4092-4164) on the GPU executor, same protocol and same keys: random inputs, ``warmup``
+    untimed slices, then single slices ``i % nslices`` (each one synchronised, as the
+    reference's eager numpy calls are) until ``max_time`` seconds or ``max_reps`` repetitions
+    are over, but at least ``min_reps``.  Returns ``time_per_slice``, ``est_time_total`` (x
+    nslices) and ``est_gigaflops`` with the reference's own flop count
+    (``total_flops(dtype)``, core.py:1196-1227: 2 flops per scalar multiply-add for float
+    dtypes, 4 for complex ones -- half of the 8-flop convention bench.py reports)."""
+    import time
+
+    torch = _torch()
+    ex = executor if executor is not None else TreeExecutor(tree, dtype=dtype, **plan_opts)
+    tdt = getattr(torch, _NP2T[ex.dtype])
+    gen = torch.Generator(device=ex.device)
+    gen.manual_seed(0)
+    tensors = []
+    for shp in ex.spec.shapes():
+        t = torch.empty(tuple(shp), dtype=tdt, device=ex.device)
+        (torch.view_as_real(t) if t.is_complex() else t).normal_(generator=gen)
+        tensors.append(t / max(1.0, float(t.numel()) ** 0.5))
+    nslices = int(ex.nslices)
+    out = torch.zeros(ex.plan.out_shape, dtype=tdt, device=ex.device)
+
+    def one(i):
+        ex.contract_device(tensors, begin=i % nslices, step=1, count=1, out=out)
+        torch.cuda.synchronize(ex.device)
+
+    for i in range(int(warmup)):
+        one(i)
+    t0 = ti = time.time()
+    i = 0
+    while (ti - t0 < max_time) or (i < min_reps):
+        one(i)
+        ti = time.time()
+        i += 1
+        if i >= max_reps:
+            break
+    time_per_slice = (ti - t0) / i
+    est_time_total = time_per_slice * nslices
+    per_mac = 4 if "complex" in ex.dtype else 2
+    total_flops = per_mac * ex.plan.macs_per_slice * nslices
+    return {
+        "time_per_slice": time_per_slice,
+        "est_time_total": est_time_total,
+        "est_gigaflops": total_flops / (1e9 * est_time_total),
+    }
+
+
 def _combine_stripped(m1, e1, m2, e2):
     """``AdderWithMaybeExponentStripped`` (cotengra/core.py:163-170) for two
     (mantissa, exponent) partial sums."""

@@ -350,6 +350,23 @@ def test_checkpointed_run_resumes(strip, tmp_path):
     assert rel_err(got, TVALS[rec["name"]]) < 1e-10
 
 
+def test_benchmark_protocol_matches_reference_keys():
+    """cb.benchmark == tree.benchmark (core.py:4092-4164): keys, repetition bounds, flop convention."""
+    rec = next(r for r in TREES if r["name"] == "lattice6x6_d3_sliced")
+    n_in = len(rec["inputs"])
+    node_inds = {int(k): v for k, v in rec["inds"].items() if int(k) >= n_in}
+    spec = cb.TreeSpec(rec["inputs"], rec["output"], rec["size_dict"], rec["path"], decode_sliced(rec["sliced"]),
+                       node_inds)
+    res = cb.benchmark(spec, dtype="complex64", max_time=0.0, min_reps=3, max_reps=5)
+    assert set(res) == {"time_per_slice", "est_time_total", "est_gigaflops"}
+    assert res["time_per_slice"] > 0 and res["est_gigaflops"] > 0
+    assert math.isclose(res["est_time_total"], res["time_per_slice"] * spec.nslices, rel_tol=1e-12)
+    ex = cb.TreeExecutor(spec, dtype="float64")
+    res2 = cb.benchmark(None, executor=ex, max_time=0.0, min_reps=2, max_reps=2)
+    flops = 2 * ex.plan.macs_per_slice * spec.nslices
+    assert math.isclose(res2["est_gigaflops"], flops / (1e9 * res2["est_time_total"]), rel_tol=1e-12)
+
+
 def test_contractor_dropin_signature():
     rec = next(r for r in TREES if r["name"] == "lattice4x4_sliced")
     spec = _spec(rec)
