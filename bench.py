@@ -25,7 +25,6 @@ network sliced further until it fits host memory/time.
 
 import argparse
 import json
-import math
 import os
 import subprocess
 import sys

@@ -28,7 +28,6 @@ The input "program" is the reference's own linear IR: the tuple of
 """
 
 import functools
-import math
 
 import numpy as np
 
