@@ -219,31 +219,54 @@ class TreeExecutor:
         Returns ``out`` or ``(out, exponent_tensor)``; asynchronous."""
         torch = _torch()
         self._check_inputs(tensors)
-        if count is None:
-            count = max(0, -(-(self.nslices - begin) // step))
+        begin, step, count = self._check_slice_range(begin, step, count)
         tdt = getattr(torch, _NP2T[self.dtype])
         with torch.cuda.device(self.device):
             if out is None:
                 out = torch.zeros(self.plan.out_shape, dtype=tdt, device=self.device)
+            elif (out.device != self.device or not out.is_contiguous() or out.dtype != tdt
+                  or tuple(out.shape) != tuple(self.plan.out_shape)):
+                raise ValueError("out must be a contiguous tensor of the plan's output shape, dtype and device")
             if self.strip_exponent and exponent is None:
                 exponent = torch.full((1,), -math.inf, dtype=torch.float64, device=self.device)
             ws = self.workspace()
-            ptrs = []
-            for t in tensors:
+            ptrs, keep = [], []
+            for i, t in enumerate(tensors):
                 if dtype_name(t.dtype) != self.dtype:
                     raise TypeError(f"plan was built for {self.dtype}, got {t.dtype}")
+                if t.device != self.device:
+                    raise ValueError(f"array {i} lives on {t.device}, the plan on {self.device}")
+                if not t.is_contiguous():
+                    # the kernels address row-major storage by the plan's own strides
+                    t = t.contiguous()
+                    keep.append(t)
                 ptrs.append(t.data_ptr())
             self.plan.execute(ptrs, out.data_ptr(), exponent.data_ptr() if exponent is not None else None,
                               ws.data_ptr(), ws.numel(), begin, step, count, _stream_ptr())
         return (out, exponent) if self.strip_exponent else out
+
+    def _check_slice_range(self, begin, step, count):
+        """Slice ids ``begin, begin+step, ...`` must all lie in ``[0, nslices)``: the device
+        decodes digits modulo the radices, so an id past the end would silently wrap and
+        count a slice twice."""
+        begin, step = int(begin), int(step)
+        if step < 1 or begin < 0:
+            raise ValueError(f"bad slice range begin={begin} step={step}")
+        if count is None:
+            count = max(0, -(-(self.nslices - begin) // step))
+        count = int(count)
+        if count < 0 or (count > 0 and begin + (count - 1) * step >= self.nslices):
+            raise ValueError(
+                f"slice ids {begin}..{begin + (count - 1) * step} (step {step}) exceed the tree's "
+                f"{self.nslices} slices")
+        return begin, step, count
 
     def contract_host(self, arrays, begin=0, step=1, count=None):
         """End-to-end with HOST buffers through ``ctgb_plan_execute_host``:
         H2D of the inputs, all slices, D2H of the result, synchronised."""
         torch = _torch()
         self._check_inputs(arrays)
-        if count is None:
-            count = max(0, -(-(self.nslices - begin) // step))
+        begin, step, count = self._check_slice_range(begin, step, count)
         host = [np.asarray(a, dtype=self.dtype, order="C") for a in arrays]
         out = np.zeros(self.plan.out_shape, dtype=self.dtype)
         with torch.cuda.device(self.device):
@@ -327,7 +350,9 @@ def benchmark(tree, dtype="float64", max_time=60, min_reps=3, max_reps=100, warm
     time_per_slice = (ti - t0) / i
     est_time_total = time_per_slice * nslices
     per_mac = 4 if "complex" in ex.dtype else 2
-    total_flops = per_mac * ex.plan.macs_per_slice * nslices
+    # tree.total_flops(dtype) counts every node of every slice (core.py:1196-1227), the
+    # slice-invariant ones included -- each timed single-slice call re-runs them here too
+    total_flops = per_mac * (ex.plan.macs_per_slice + ex.plan.macs_invariant) * nslices
     return {
         "time_per_slice": time_per_slice,
         "est_time_total": est_time_total,
@@ -440,7 +465,7 @@ class B200Contractor:
         return cls(spec.contractions(), **kw)
 
     def _executor(self, shapes, dtype, strip):
-        key = (shapes, dtype, strip)
+        key = (shapes, dtype, strip, _torch().cuda.current_device())
         ex = self._plans.get(key)
         if ex is None:
             # synthesise a flat (unsliced) network whose inputs are the given arrays
@@ -465,8 +490,9 @@ class B200Contractor:
         tensors = [d[0] for d in devs]
         as_numpy = all(d[1] for d in devs)
         dtype = _common_dtype(*tensors)
-        ex = self._executor(tuple(tuple(t.shape) for t in tensors), dtype, strip)
-        res = ex.run(tensors)
+        with torch.cuda.device(tensors[0].device if tensors else torch.cuda.current_device()):
+            ex = self._executor(tuple(tuple(t.shape) for t in tensors), dtype, strip)
+            res = ex.run([t.to(ex.device) for t in tensors])
         if strip:
             m, e = res
             e = float(e.item())
@@ -495,11 +521,12 @@ class _FlatExecutor:
 
     def run(self, tensors):
         torch = _torch()
-        out = torch.zeros(self.plan.out_shape, dtype=self.tdt, device=self.device)
-        exp = torch.full((1,), -math.inf, dtype=torch.float64, device=self.device) if self.strip else None
-        self.plan.execute([t.data_ptr() for t in tensors], out.data_ptr(),
-                          exp.data_ptr() if exp is not None else None, self.ws.data_ptr(),
-                          self.ws.numel(), 0, 1, 1, _stream_ptr())
+        with torch.cuda.device(self.device):
+            out = torch.zeros(self.plan.out_shape, dtype=self.tdt, device=self.device)
+            exp = torch.full((1,), -math.inf, dtype=torch.float64, device=self.device) if self.strip else None
+            self.plan.execute([t.data_ptr() for t in tensors], out.data_ptr(),
+                              exp.data_ptr() if exp is not None else None, self.ws.data_ptr(),
+                              self.ws.numel(), 0, 1, 1, _stream_ptr())
         return (out, exp) if self.strip else out
 
 

@@ -16,6 +16,7 @@
 //     added (split-K).
 #pragma once
 #include <cuda_runtime.h>
+#include <math_constants.h>
 #include <stdint.h>
 
 #include "gett_desc.h"
@@ -543,9 +544,13 @@ template <typename T>
 __global__ void strip_kernel(T* __restrict__ p, long long n, const unsigned long long* __restrict__ slot,
                              double* __restrict__ exponent) {
   const double f = __longlong_as_double((long long)*slot);
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
-    p[i] = scale_of(p[i], f);
-  if (blockIdx.x == 0 && threadIdx.x == 0) *exponent += log10(f);
+  // an all-zero intermediate (contract.py:819-820, check_zero): keep the zeros instead of 0/0
+  // and make the exponent -inf; it stays -inf through every later node of the slice, and the
+  // exponent-aware adder below gives such a slice weight 10^-inf = 0 (core.py:163-170)
+  if (f != 0.0)
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+      p[i] = scale_of(p[i], f);
+  if (blockIdx.x == 0 && threadIdx.x == 0) *exponent += (f != 0.0) ? log10(f) : -CUDART_INF;
 }
 
 __device__ __forceinline__ float mulr_of(float v, double s) { return (float)(v * s); }

@@ -393,9 +393,8 @@ def build_pair_desc(dims: PairDims, dtype, accumulate=False, sm_count=148,
     if variant == VAR_DMMASTREAM and not (dtype == "complex128" and N <= 32 and K <= 32 and B == 1 and M < 1 << 32):
         variant = VAR_DMMA_256x16
     if variant == VAR_ROWSTREAM:
-        # the streaming kernel needs exact tiles: every m dim must divide
-        ok = N <= 8 and K <= 8 and B == 1 and M < 1 << 32 and all(
-            d[0] <= 256 or d[0] % 256 == 0 or True for d in m)
+        # (a ragged blocked m dim is caught after tiling, below)
+        ok = N <= 8 and K <= 8 and B == 1 and M < 1 << 32
         if not ok:
             variant = VAR_ROW_256x4 if N <= 4 else VAR_ROW_128x8
     MT, NT, KT = VARIANT_TILES[variant]

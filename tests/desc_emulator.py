@@ -194,8 +194,10 @@ def emulate_plan(plan, arrays, slice_ids=None):
                 if plan.strip_exponent:
                     n = math.prod(nd["c"].shape)
                     f = np.max(np.abs(c[:n]))
+                    # strip_kernel: an all-zero intermediate keeps its zeros, exponent -> -inf
                     exp += math.log10(f) if f > 0 else -math.inf
-                    c[:n] = c[:n] / f
+                    if f > 0:
+                        c[:n] = c[:n] / f
             else:
                 emulate_single(nd["words"], a, c)
         return exp

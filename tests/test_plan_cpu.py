@@ -81,3 +81,27 @@ def test_arena_never_overlaps_live_tensors():
         for s in (nd["a"], nd["b"]):
             if s is not None and s.kind == 1 and s.last_use == nd["pos"]:
                 live.pop(id(s), None)
+
+
+@pytest.mark.parametrize("name,which", [("lattice6x6_d3_sliced", 0), ("rand_r3_o0_hi0_ho1_root_s666_sliced", 1)])
+def test_zero_slices_keep_the_sum_finite(name, which):
+    """check_zero (contract.py:819-820): a slice with an all-zero intermediate is
+    (0, -inf) and drops out of the exponent-aware sum (core.py:163-170) instead of
+    poisoning it with 0/0.  (The zeroed digit belongs to an *inner* sliced index: when every
+    slice of one output chunk is zero the reference's adder itself forms 10**(-inf - -inf) = nan,
+    core.py:163-170; the device path returns the zeros.)"""
+    from oracle import ctg_oracle as orc
+    from tests.zero_util import zero_one_digit
+
+    rec = next(r for r in TREES if r["name"] == name)
+    spec, plan = _plan(rec, strip_exponent=True)
+    arrays, _ = zero_one_digit(spec, make_arrays(spec.shapes(), rec["dtype"], seed=rec["seed"]), which)
+    wm, we = orc.contract_tree([tuple(t) for t in spec.inputs], spec.output, spec.sliced,
+                               spec.contractions(), arrays, strip_exponent=True, check_zero=True)
+    m, e = emulate_plan(plan, arrays)
+    assert np.all(np.isfinite(m)) and np.isfinite(e)
+    assert rel_err(m * 10.0**e, wm * 10.0**we) < 1e-10
+    # every slice zero: mantissa zeros, exponent -inf
+    zeros = [np.zeros_like(a) for a in arrays]
+    m0, e0 = emulate_plan(plan, zeros)
+    assert e0 == -np.inf and not np.any(m0)
