@@ -27,6 +27,7 @@ from .contract import (
     contract_distributed,
     contract_tree,
     einsum,
+    gen_output_chunks,
     implementation,
     install,
     make_contractor,
@@ -38,6 +39,6 @@ from .contract import (
 __all__ = [
     "TreeSpec", "get_symbol", "PairDims", "build_pair_desc", "build_single_desc",
     "classify_pair", "classify_single", "ExecPlan", "B200Contractor", "TreeExecutor",
-    "benchmark", "contract_checkpointed", "contract_distributed", "contract_tree", "einsum", "implementation", "install",
+    "benchmark", "contract_checkpointed", "contract_distributed", "contract_tree", "einsum", "gen_output_chunks", "implementation", "install",
     "make_contractor", "rank_slices", "reduce_partials", "tensordot",
 ]

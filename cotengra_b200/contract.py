@@ -10,6 +10,7 @@ behaviour as cotengra's execution path, backed by the sm_100a kernels.
                                        :840 ``CuQuantumContractor`` (whole-tree)
     contract_tree(tree, arrays) ...... cotengra/core.py:3943 ``ContractionTree.contract``
     contract_distributed(...) ........ cotengra/core.py:4032 ``contract_mpi`` (NCCL)
+    gen_output_chunks(tree, arrays) .. cotengra/core.py:3884 ``gen_output_chunks``
     install(tree) .................... seeds ``tree.contraction_cores`` (core.py:3699)
 
 Arrays may be numpy arrays (copied to the GPU and back: the host path) or torch
@@ -27,7 +28,7 @@ import math
 import numpy as np
 
 from . import _lib, lowering
-from .executor import ExecPlan
+from .executor import ExecPlan, output_chunking
 from .lowering import (
     build_pair_desc,
     build_single_desc,
@@ -180,9 +181,18 @@ class TreeExecutor:
     """
 
     def __init__(self, tree, dtype="complex128", strip_exponent=False, device=None,
-                 contractions=None, **plan_opts):
+                 contractions=None, fuse=True, **plan_opts):
         self.spec = tree if isinstance(tree, TreeSpec) else TreeSpec.from_cotengra(tree)
-        ir = self.spec.contractions() if contractions is None else contractions
+        # stem fusion (fusion.py): an execution-plan transformation of the tree cotengra found --
+        # big stem tensors absorb pre-contracted groups of small tensors in one pass.  ``spec``
+        # stays the caller's tree; ``exec_spec`` is what runs.  ``fuse=False`` executes the
+        # reference's own node sequence one to one.
+        self.exec_spec, self.fusion = self.spec, {"changed": False}
+        if fuse and contractions is None:
+            from .fusion import fuse_stems
+
+            self.exec_spec, self.fusion = fuse_stems(self.spec, dtype_name(dtype))
+        ir = self.exec_spec.contractions() if contractions is None else contractions
         torch = _torch()
         self.device = torch.device("cuda", torch.cuda.current_device() if device is None else device)
         with torch.cuda.device(self.device):
@@ -192,6 +202,21 @@ class TreeExecutor:
         self.dtype = self.plan.dtype
         self.strip_exponent = bool(strip_exponent)
         self._ws = None
+        self._ref_work = None
+
+    @property
+    def reference_work(self):
+        """``(macs_per_slice, macs_invariant, elements_per_slice)`` of the caller's (unfused)
+        tree -- the algorithmic work throughput figures are quoted on."""
+        if self._ref_work is None:
+            if self.fusion.get("changed"):
+                from .fusion import tree_work
+
+                self._ref_work = tree_work(self.spec)
+            else:
+                self._ref_work = (self.plan.macs_per_slice, self.plan.macs_invariant,
+                                  self.plan.elements_per_slice)
+        return self._ref_work
 
     @property
     def nslices(self):
@@ -278,6 +303,57 @@ class TreeExecutor:
     def __call__(self, arrays, **kw):
         return contract_tree(self, arrays, **kw)
 
+    # ------------------------------------------------------------------ output chunks
+    def _chunk_plan(self):
+        """A second plan over the same program whose output is ONE chunk: the output term
+        without its sliced indices, so that every sliced index is summed.  Executed over the
+        ``stepsize`` consecutive slice ids of a chunk (core.py:3916-3935)."""
+        if getattr(self, "_chunk", None) is None:
+            torch = _torch()
+            spec = self.exec_spec
+            chunk_out, _step, _n = output_chunking(spec)
+            with torch.cuda.device(self.device):
+                self._chunk = ExecPlan(spec.contractions(), spec.inputs, chunk_out, spec.size_dict,
+                                       spec.sliced, dtype=self.dtype,
+                                       strip_exponent=self.strip_exponent).create()
+        return self._chunk
+
+    def gen_output_chunks(self, arrays, with_key=False):
+        """``tree.gen_output_chunks(arrays, with_key)`` (cotengra/core.py:3884-3941): yield
+        every output chunk -- one per setting of the sliced *output* indices -- after its
+        inner slices have been summed on the device, without ever forming the full output.
+        Like the reference this needs the sliced indices ordered output-first (the default
+        order, core.py:99-104); unlike it, ``strip_exponent`` chunks are summed with the
+        exponent-aware adder and come as ``(mantissa, exponent)``.
+        numpy in -> numpy chunks; torch CUDA in -> torch CUDA chunks (a fresh tensor each)."""
+        torch = _torch()
+        self._check_inputs(arrays)
+        spec = self.spec
+        _chunk_out, stepsize, nchunks = output_chunking(spec)
+        plan = self._chunk_plan()
+        all_numpy = all(not isinstance(a, torch.Tensor) for a in arrays)
+        tensors = [_to_device(a, self.device)[0] for a in arrays]
+        ptrs = [t.data_ptr() for t in tensors]
+        tdt = getattr(torch, _NP2T[self.dtype])
+        need = plan.total_bytes
+        with torch.cuda.device(self.device):
+            ws = torch.empty(max(need, 1), dtype=torch.uint8, device=self.device)
+        for o in range(nchunks):
+            with torch.cuda.device(self.device):
+                out = torch.zeros(plan.out_shape, dtype=tdt, device=self.device)
+                exp = (torch.full((1,), -math.inf, dtype=torch.float64, device=self.device)
+                       if self.strip_exponent else None)
+                plan.execute(ptrs, out.data_ptr(), exp.data_ptr() if exp is not None else None,
+                             ws.data_ptr(), ws.numel(), o * stepsize, 1, stepsize, _stream_ptr())
+            chunk = _from_device(out, all_numpy)
+            if self.strip_exponent:
+                chunk = (chunk, float(exp.item()))
+            if with_key:
+                key = {ix: x for ix, x in spec.slice_key(o * stepsize).items() if ix in spec.output}
+                yield chunk, key
+            else:
+                yield chunk
+
 
 def contract_tree(tree, arrays, strip_exponent=False, check_zero=False, dtype=None,
                   slice_ids=None, **plan_opts):
@@ -306,6 +382,18 @@ def contract_tree(tree, arrays, strip_exponent=False, check_zero=False, dtype=No
         m, e = res
         return _finish_stripped(m, float(e.item()), check_zero)
     return res
+
+
+def gen_output_chunks(tree, arrays, with_key=False, strip_exponent=False, dtype=None, **plan_opts):
+    """``tree.gen_output_chunks(arrays, with_key=...)`` (cotengra/core.py:3884-3941) on the
+    GPU executor; see ``TreeExecutor.gen_output_chunks``."""
+    if isinstance(tree, TreeExecutor):
+        ex = tree
+    else:
+        if dtype is None:
+            dtype = dtype_name(arrays[0].dtype)
+        ex = TreeExecutor(tree, dtype=dtype, strip_exponent=strip_exponent, **plan_opts)
+    yield from ex.gen_output_chunks(arrays, with_key=with_key)
 
 
 def benchmark(tree, dtype="float64", max_time=60, min_reps=3, max_reps=100, warmup=True,
@@ -352,7 +440,8 @@ def benchmark(tree, dtype="float64", max_time=60, min_reps=3, max_reps=100, warm
     per_mac = 4 if "complex" in ex.dtype else 2
     # tree.total_flops(dtype) counts every node of every slice (core.py:1196-1227), the
     # slice-invariant ones included -- each timed single-slice call re-runs them here too
-    total_flops = per_mac * (ex.plan.macs_per_slice + ex.plan.macs_invariant) * nslices
+    macs_v, macs_i, _el = ex.reference_work
+    total_flops = per_mac * (macs_v + macs_i) * nslices
     return {
         "time_per_slice": time_per_slice,
         "est_time_total": est_time_total,

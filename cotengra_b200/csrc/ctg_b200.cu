@@ -166,16 +166,27 @@ template <typename T>
 int launch_dotstream(const int64_t* h, const int64_t* d, const void* A, const void* B, void* C, cudaStream_t st) {
   DevInfo& di = devinfo();
   if (!di.ok) return fail(CTGB_E_CUDA, "no CUDA device");
-  if (h[W_MTA] != 1 || h[W_NTA] != 1 || h[W_TILES_M] != 1 || h[W_TILES_N] != 1 || h[W_TILES_B] != 1 ||
-      h[W_KTA] > DOT_KT || h[W_NGK] > 64 || h[W_STEPS_K] >= (1ll << 31) ||
+  const bool mn = h[W_VARIANT] == VAR_DOTSTREAM4;
+  const int lim = mn ? DOT4_MN : 1, kt = mn ? DOT4_KT : DOT_KT;
+  if (h[W_MTA] > lim || h[W_NTA] > lim || h[W_TILES_M] != 1 || h[W_TILES_N] != 1 || h[W_TILES_B] != 1 ||
+      h[W_KTA] > kt || h[W_NGK] > 64 || h[W_STEPS_K] >= (1ll << 31) || h[W_PGM] >= 0 || h[W_PGN] >= 0 ||
       (h[W_PGK] >= 0 && (h[W_KFULL] % h[W_KTEXT]) != 0))
     return fail(CTGB_E_VALUE, "descriptor does not fit the dot-stream kernel");
   if (h[W_STEPS_K] == 0) return CTGB_OK;
-  if (!(h[W_FLAGS] & 1)) CUDA_TRY(cudaMemsetAsync(C, 0, sizeof(T), st));
+  if (!(h[W_FLAGS] & 1)) {
+    // block partial sums are added atomically: a dense result is zeroed first
+    const long long celems = h[W_MTA] * h[W_NTA];
+    if (celems > 1 && h[W_CELEMS] != celems) return fail(CTGB_E_VALUE, "dot-stream into a strided C needs accumulate");
+    CUDA_TRY(cudaMemsetAsync(C, 0, (size_t)celems * sizeof(T), st));
+  }
   unsigned long long blocks = (unsigned long long)h[W_STEPS_K];
-  const unsigned long long cap = (unsigned long long)di.sms * 2;  // two resident blocks per SM, one wave
+  // one wave: two resident blocks per SM (one for the 16-accumulator variant)
+  const unsigned long long cap = (unsigned long long)di.sms * (mn ? 1 : 2);
   if (blocks > cap) blocks = cap;
-  dotstream_kernel<T><<<(unsigned)blocks, DOT_THREADS, 0, st>>>(d, (const T*)A, (const T*)B, (T*)C);
+  if (mn)
+    dotstream_kernel<T, DOT4_MN, DOT4_MN, DOT4_U><<<(unsigned)blocks, DOT_THREADS, 0, st>>>(d, (const T*)A, (const T*)B, (T*)C);
+  else
+    dotstream_kernel<T, 1, 1, DOT_U><<<(unsigned)blocks, DOT_THREADS, 0, st>>>(d, (const T*)A, (const T*)B, (T*)C);
   g_launches.fetch_add(1, std::memory_order_relaxed);
   CUDA_TRY(cudaGetLastError());
   return CTGB_OK;
@@ -281,7 +292,7 @@ int launch_gett_typed(const int64_t* h, const int64_t* d, const void* A, const v
   const int variant = (int)h[W_VARIANT];
   if (variant == VAR_ROWSTREAM) return launch_rowstream<T>(h, d, A, B, C, st);
   if (variant == VAR_DMMASTREAM) return launch_dmmastream(h, d, A, B, C, st);
-  if (variant == VAR_DOTSTREAM) return launch_dotstream<T>(h, d, A, B, C, st);
+  if (variant == VAR_DOTSTREAM || variant == VAR_DOTSTREAM4) return launch_dotstream<T>(h, d, A, B, C, st);
   if constexpr (std::is_same<T, float2>::value) {
     if (variant == VAR_TC05_128x64) return launch_tc05<64>(h, d, A, B, C, st);
     if (variant == VAR_TC05_128x32) return launch_tc05<32>(h, d, A, B, C, st);

@@ -14,20 +14,51 @@
 #pragma once
 
 constexpr int DOT_KT = 2048, DOT_THREADS = 256, DOT_U = DOT_KT / DOT_THREADS;
+// the same stream with a small kept space on both operands (M, N <= 4): the last small tensor
+// of a stem peeled over the final inner product (cotengra_b200/fusion.py),
+//   R[m, n] = sum_k A[k, m] * B[k, n],
+// 16 accumulators per thread, 2 k per thread and tile (8 + 8 loads in flight)
+constexpr int DOT4_MN = 4, DOT4_U = 2, DOT4_KT = DOT4_U * DOT_THREADS;
 
-template <typename T>
-__global__ void __launch_bounds__(DOT_THREADS, 2)
+template <typename T, int MT, int NT, int U>
+__global__ void __launch_bounds__(DOT_THREADS, (MT * NT > 1) ? 1 : 2)
 dotstream_kernel(const int64_t* __restrict__ D, const T* __restrict__ A, const T* __restrict__ B, T* __restrict__ C) {
-  __shared__ T s_part[DOT_THREADS / 32];
+  __shared__ T s_part[DOT_THREADS / 32][MT * NT];
   const int tid = threadIdx.x, lane = tid & 31;
   const int n_tk = (int)D[W_NTK], n_gk = (int)D[W_NGK];
-  const int KTa = (int)D[W_KTA];
+  const int KTa = (int)D[W_KTA], MTa = (int)D[W_MTA], NTa = (int)D[W_NTA];
   const unsigned steps = (unsigned)D[W_STEPS_K];  // the host guarantees < 2^31
-  // tile-local offsets of this thread's elements (tile dims: dim 0 fastest)
-  long long la[DOT_U], lb[DOT_U];
-  bool in_tile[DOT_U];
+  // offsets of the kept indices (all of M and N sit inside the tile)
+  long long am[MT], bn[NT];
 #pragma unroll
-  for (int j = 0; j < DOT_U; ++j) {
+  for (int i = 0; i < MT; ++i) {
+    long long a = 0;
+    unsigned e = (unsigned)i;
+    if (MT > 1 && i < MTa)
+      for (int d = 0; d < (int)D[W_NTM]; ++d) {
+        const int64_t* L = D + OFF_TM + d * 3;
+        a += (long long)(e % (unsigned)L[0]) * L[1];
+        e /= (unsigned)L[0];
+      }
+    am[i] = a;
+  }
+#pragma unroll
+  for (int i = 0; i < NT; ++i) {
+    long long b = 0;
+    unsigned e = (unsigned)i;
+    if (NT > 1 && i < NTa)
+      for (int d = 0; d < (int)D[W_NTN]; ++d) {
+        const int64_t* L = D + OFF_TN + d * 3;
+        b += (long long)(e % (unsigned)L[0]) * L[1];
+        e /= (unsigned)L[0];
+      }
+    bn[i] = b;
+  }
+  // tile-local offsets of this thread's elements (tile dims: dim 0 fastest)
+  long long la[U], lb[U];
+  bool in_tile[U];
+#pragma unroll
+  for (int j = 0; j < U; ++j) {
     unsigned e = (unsigned)(tid + j * DOT_THREADS);
     in_tile[j] = e < (unsigned)KTa;
     if (!in_tile[j]) e = 0;
@@ -57,7 +88,11 @@ dotstream_kernel(const int64_t* __restrict__ D, const T* __restrict__ A, const T
       g_sb[h] = G[3];
     }
   }
-  T acc = zero_of<T>();
+  T acc[MT][NT];
+#pragma unroll
+  for (int i = 0; i < MT; ++i)
+#pragma unroll
+    for (int c = 0; c < NT; ++c) acc[i][c] = zero_of<T>();
   for (unsigned t = blockIdx.x; t < steps; t += gridDim.x) {
     long long ta = 0, tb = 0;
 #pragma unroll
@@ -68,23 +103,51 @@ dotstream_kernel(const int64_t* __restrict__ D, const T* __restrict__ A, const T
     }
     ta = warp_sum_ll(ta);
     tb = warp_sum_ll(tb);
-    T a[DOT_U], b[DOT_U];
+    T a[U][MT], b[U][NT];
 #pragma unroll
-    for (int j = 0; j < DOT_U; ++j) {
-      a[j] = in_tile[j] ? A[ta + la[j]] : zero_of<T>();
-      b[j] = in_tile[j] ? B[tb + lb[j]] : zero_of<T>();
+    for (int j = 0; j < U; ++j) {
+#pragma unroll
+      for (int i = 0; i < MT; ++i) a[j][i] = (in_tile[j] && i < MTa) ? A[ta + la[j] + am[i]] : zero_of<T>();
+#pragma unroll
+      for (int c = 0; c < NT; ++c) b[j][c] = (in_tile[j] && c < NTa) ? B[tb + lb[j] + bn[c]] : zero_of<T>();
     }
 #pragma unroll
-    for (int j = 0; j < DOT_U; ++j) mac(acc, a[j], b[j]);
-  }
-  // block reduction, one atomic per block
+    for (int j = 0; j < U; ++j)
 #pragma unroll
-  for (int d = 16; d > 0; d >>= 1) acc = add_of(acc, shfl_down_of(acc, d));
-  if (lane == 0) s_part[tid >> 5] = acc;
+      for (int i = 0; i < MT; ++i)
+#pragma unroll
+        for (int c = 0; c < NT; ++c) mac(acc[i][c], a[j][i], b[j][c]);
+  }
+  // block reduction, one atomic per block and output element
+#pragma unroll
+  for (int i = 0; i < MT; ++i)
+#pragma unroll
+    for (int c = 0; c < NT; ++c) {
+      T v = acc[i][c];
+#pragma unroll
+      for (int d = 16; d > 0; d >>= 1) v = add_of(v, shfl_down_of(v, d));
+      if (lane == 0) s_part[tid >> 5][i * NT + c] = v;
+    }
   __syncthreads();
-  if (tid == 0) {
-    T v = s_part[0];
-    for (int w = 1; w < DOT_THREADS / 32; ++w) v = add_of(v, s_part[w]);
-    atomic_add_of(C, v);
+  if (tid < MT * NT) {
+    const int i = tid / NT, c = tid % NT;
+    if (i < MTa && c < NTa) {
+      T v = s_part[0][tid];
+      for (int w = 1; w < DOT_THREADS / 32; ++w) v = add_of(v, s_part[w][tid]);
+      long long oc = 0;
+      unsigned e = (unsigned)i;
+      for (int d = 0; d < (int)D[W_NTM]; ++d) {
+        const int64_t* L = D + OFF_TM + d * 3;
+        oc += (long long)(e % (unsigned)L[0]) * L[2];
+        e /= (unsigned)L[0];
+      }
+      e = (unsigned)c;
+      for (int d = 0; d < (int)D[W_NTN]; ++d) {
+        const int64_t* L = D + OFF_TN + d * 3;
+        oc += (long long)(e % (unsigned)L[0]) * L[2];
+        e /= (unsigned)L[0];
+      }
+      atomic_add_of(C + oc, v);
+    }
   }
 }

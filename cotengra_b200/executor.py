@@ -90,6 +90,27 @@ class _Arena:
         self.free = merged
 
 
+def output_chunking(spec):
+    """Host-side geometry of ``gen_output_chunks`` (cotengra/core.py:3884-3941) for a
+    ``TreeSpec``: ``(chunk_output, stepsize, nchunks)`` -- the output term of one chunk (the
+    sliced output indices removed), the number of consecutive slice ids summed into a chunk
+    (product of the inner sliced extents) and the number of chunks.  Raises ``ValueError``
+    when the sliced indices are not ordered output-first (core.py:3912-3913)."""
+    inner_seen = False
+    for ind, _size, _proj in spec.sliced:
+        if ind in spec.output:
+            if inner_seen:
+                raise ValueError("gen_output_chunks needs the sliced indices sorted output-first "
+                                 "(core.py:3912-3913)")
+        else:
+            inner_seen = True
+    sliced = {s[0] for s in spec.sliced}
+    chunk_out = tuple(ix for ix in spec.output if ix not in sliced)
+    stepsize = math.prod(size for ind, size, proj in spec.sliced
+                         if ind not in spec.output and proj is None)
+    return chunk_out, stepsize, spec.nslices // stepsize
+
+
 class _T:
     """A tensor slot while planning."""
 

@@ -105,3 +105,31 @@ def test_zero_slices_keep_the_sum_finite(name, which):
     zeros = [np.zeros_like(a) for a in arrays]
     m0, e0 = emulate_plan(plan, zeros)
     assert e0 == -np.inf and not np.any(m0)
+
+
+SLICED_OUT = [r["name"] for r in TREES if r["name"].endswith("_sliced_out") and r["name"] in TVALS] + ["projected"]
+
+
+@pytest.mark.parametrize("name", SLICED_OUT)
+def test_output_chunks_geometry(name):
+    """gen_output_chunks (core.py:3884-3941): chunk o = sum of slice ids [o*step, (o+1)*step)
+    of a plan whose output term has no sliced index; stacked by key they give the full result."""
+    from cotengra_b200.executor import output_chunking
+
+    rec = next(r for r in TREES if r["name"] == name)
+    spec, _ = _plan(rec)
+    chunk_out, step, nchunks = output_chunking(spec)
+    plan = ExecPlan(spec.contractions(), spec.inputs, chunk_out, spec.size_dict, spec.sliced,
+                    dtype=rec["dtype"], sm_count=8)
+    arrays = make_arrays(spec.shapes(), rec["dtype"], seed=rec["seed"])
+    want = TVALS[name]
+    assert step * nchunks == spec.nslices
+    for o in range(nchunks):
+        got = emulate_plan(plan, arrays, slice_ids=range(o * step, (o + 1) * step))
+        key = spec.slice_key(o * step)
+        sel = tuple(key[ix] if (ix in key and spec.sliced[[s[0] for s in spec.sliced].index(ix)][2] is None)
+                    else slice(None) for ix in spec.output)
+        ref = want[sel]
+        # projected output indices keep extent 1 in the full result
+        ref = ref.reshape(got.shape)
+        assert rel_err(got, ref) < 1e-11
