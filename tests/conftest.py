@@ -13,6 +13,9 @@ def pytest_configure(config):
         "markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)"
     )
     config.addinivalue_line(
+        "markers", "multigpu: needs >= 2 GPUs on the box (gpurun --gpus N); skipped otherwise"
+    )
+    config.addinivalue_line(
         "markers",
         "reference: needs the unmodified reference at /root/reference "
         "(build container only; auto-skipped elsewhere)",

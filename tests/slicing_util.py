@@ -60,3 +60,13 @@ def slice_id(spec, key):
         if project is None:
             i += key[ind] * stride
     return i
+
+
+def appxB_at_width(width_log2):
+    """The Sycamore-m20 Appendix-B tree (W = 2^30 as benchmarked), sliced further to
+    W = 2^width_log2 for smaller widths -- the trees of ``tests/golden/big_slices.json``."""
+    from tests.helpers import decode_sliced, load_json
+
+    rec = next(r for r in load_json("sycamore_m20.json") if r["name"] == "sycamore_m20_appxB")
+    spec = TreeSpec(rec["inputs"], rec["output"], rec["size_dict"], rec["path"], decode_sliced(rec["sliced"]))
+    return spec if width_log2 >= 30 else slice_to_width(spec, 2 ** width_log2)

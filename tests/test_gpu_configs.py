@@ -42,10 +42,15 @@ def test_config2_peps8x8_bond6():
     want = orc.run_contractions(spec.contractions(), arrays)  # numpy oracle, complex128
     got = cb.contract_tree(spec, arrays)
     assert rel_err(got, want) < 1e-10
-    got64 = cb.contract_tree(spec, [a.astype(np.complex64) for a in arrays])
+    a64 = [a.astype(np.complex64) for a in arrays]
+    got64 = cb.contract_tree(spec, a64)
     assert got64.dtype == np.complex64
-    # the reference's own c64 and c128 runs differ by 8e-6 on this network
-    assert rel_err(got64, want) < 5e-5
+    # north_star: 1e-5 -- or, where the reference's own numpy complex64 run is itself further than
+    # that from the complex128 value (8e-6 on this network), within 3x of its error
+    e_ref = rel_err(orc.run_contractions(spec.contractions(), a64), want)
+    e_gpu = rel_err(got64, want)
+    print(f"config2 peps8x8 D=6 c64: gpu {e_gpu:.2e}, numpy c64 {e_ref:.2e}")
+    assert e_gpu < max(1e-5, 3.0 * e_ref)
 
 
 def test_config3_sycamore_m10_amplitude():
@@ -54,8 +59,12 @@ def test_config3_sycamore_m10_amplitude():
     want = vals["m10_amplitude"]  # reference numpy path, real gate tensors
     got = cb.contract_tree(spec, arrays)
     assert rel_err(got, want) < 1e-10
-    got64 = cb.contract_tree(spec, [a.astype(np.complex64) for a in arrays])
-    assert rel_err(got64, want) < 1e-4
+    a64 = [a.astype(np.complex64) for a in arrays]
+    got64 = cb.contract_tree(spec, a64)
+    e_ref = rel_err(orc.run_contractions(spec.contractions(), a64), want)
+    e_gpu = rel_err(got64, want)
+    print(f"config3 m10 c64: gpu {e_gpu:.2e}, numpy c64 {e_ref:.2e}")
+    assert e_gpu < max(1e-5, 3.0 * e_ref)
     # slices of the further-sliced copy against the reference
     small = cb.TreeSpec.from_dict(rec["small_spec"])
     ex = cb.TreeExecutor(small, dtype="complex128")

@@ -314,11 +314,16 @@ def test_trees_golden(rec):
         assert rel_err(m * 10.0**e, want) < 1e-10
         wm, we = TVALS[rec["name"] + "_m"], float(TVALS[rec["name"] + "_e"])
         assert rel_err(m * 10.0 ** (e - we), wm) < 1e-10
-    # single precision against the double precision reference
+    # single precision: as close to the double-precision reference value as the reference's own
+    # numpy single-precision path is (within 3x), and within 1e-5 wherever that path is -- any fp32
+    # evaluation of a whole tree loses digits with depth and cancellation (per node: 1e-5, above)
     lo = "complex64" if np.dtype(rec["dtype"]).kind == "c" else "float32"
-    got32 = cb.contract_tree(spec, [_cast(a, lo) for a in arrays])
+    lo_arrays = [_cast(a, lo) for a in arrays]
+    got32 = cb.contract_tree(spec, lo_arrays)
     assert got32.dtype == np.dtype(lo)
-    assert rel_err(got32, want) < 2e-4  # long fp32 chains; per-node bound is 1e-5
+    ref32 = orc.contract_tree([tuple(t) for t in spec.inputs], spec.output, spec.sliced,
+                              spec.contractions(), lo_arrays)
+    assert rel_err(got32, want) < max(1e-5, 3.0 * rel_err(ref32, want))
 
 
 @pytest.mark.parametrize("strip", [False, True])
@@ -363,7 +368,8 @@ def test_benchmark_protocol_matches_reference_keys():
     assert math.isclose(res["est_time_total"], res["time_per_slice"] * spec.nslices, rel_tol=1e-12)
     ex = cb.TreeExecutor(spec, dtype="float64")
     res2 = cb.benchmark(None, executor=ex, max_time=0.0, min_reps=2, max_reps=2)
-    flops = 2 * ex.plan.macs_per_slice * spec.nslices
+    macs_v, macs_i, _el = ex.reference_work  # tree.total_flops counts the hoisted nodes too
+    flops = 2 * (macs_v + macs_i) * spec.nslices
     assert math.isclose(res2["est_gigaflops"], flops / (1e9 * res2["est_time_total"]), rel_tol=1e-12)
 
 
@@ -423,7 +429,16 @@ def test_sycamore_slices_vs_reference_and_oracle():
     dev32 = [torch.from_numpy(a.astype(np.complex64)).cuda() for a in arrays]
     m32, e32 = ex32.contract_device(dev32, begin=0, step=1, count=1)
     got32 = m32.cpu().numpy() * 10.0 ** (float(e32.item()) - we)
-    assert rel_err(got32, wm) < 1e-4
+    # judged against the reference's own numpy complex64 path on the same slice (see test_trees_golden)
+    rm, re_ = orc.run_contractions(
+        decode_ir(rec["contractions"]),
+        orc.slice_arrays(inputs, decode_sliced(rec["sliced"]), [a.astype(np.complex64) for a in arrays], 0),
+        strip_exponent=True,
+    )
+    e_ref = rel_err(rm.astype(np.complex128) * 10.0 ** (float(re_) - we), wm)
+    e_gpu = rel_err(got32, wm)
+    print(f"sycamore_m20_medium c64: gpu {e_gpu:.2e}, numpy c64 {e_ref:.2e}")
+    assert e_gpu < max(1e-5, 3.0 * e_ref)
 
 
 def test_large_slice_properties():
