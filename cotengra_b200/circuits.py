@@ -97,3 +97,73 @@ def amplitude_network(path, bits=None, dtype="complex128"):
         arrays.append(v)
     size_dict = {ix: 2 for term in inputs for ix in term}
     return inputs, (), size_dict, arrays
+
+
+def rank_simplify(inputs, output, size_dict, arrays, max_rounds=64):
+    """Absorb low-rank tensors into their neighbours before the tree search -- the
+    ``rank_simplify`` step quimb applies in the reference notebooks (the m10 network drops
+    from 1764 to ~160 tensors, ``examples/Quantum Circuit Example Old.ipynb:143``; the
+    shipped m20 benchmark JSON with 381 tensors is the product of the same step).
+
+    Two tensors that share an index are merged whenever the result's rank does not exceed
+    the larger of the two ranks (vectors into anything, matrices into anything, gates that
+    act on the same qubit pair into each other), until nothing changes.  This is network
+    *construction* on the host (numpy, tensors of <= 2^8 elements), not part of the
+    contraction path.  Returns ``(inputs, output, size_dict, arrays)`` with the surviving
+    index labels unchanged."""
+    output = tuple(output)
+    terms = {i: tuple(t) for i, t in enumerate(inputs)}
+    data = {i: np.asarray(a) for i, a in enumerate(arrays)}
+    where = {}
+    for i, t in terms.items():
+        for ix in t:
+            where.setdefault(ix, set()).add(i)
+    nxt = len(terms)
+
+    def merge(i, j):
+        nonlocal nxt
+        ti, tj = terms[i], terms[j]
+        shared = [ix for ix in ti if ix in tj]
+        # an index survives if it is an output index or lives on a third tensor
+        gone = [ix for ix in shared if ix not in output and where[ix] <= {i, j}]
+        keep = [ix for ix in ti if ix not in gone] + [ix for ix in tj if ix not in gone and ix not in ti]
+        return keep, gone
+
+    for _ in range(max_rounds):
+        changed = False
+        for i in sorted(terms, key=lambda k: len(terms[k])):
+            if i not in terms:
+                continue
+            best = None
+            for ix in terms[i]:
+                for j in where[ix]:
+                    if j == i or j not in terms:
+                        continue
+                    keep, gone = merge(i, j)
+                    if gone and len(keep) <= max(len(terms[i]), len(terms[j])):
+                        if best is None or len(keep) < len(best[1]):
+                            best = (j, keep)
+            if best is None:
+                continue
+            j, keep = best
+            sym = {}
+            for ix in terms[i] + terms[j]:
+                sym.setdefault(ix, chr(ord("a") + len(sym)) if len(sym) < 26 else chr(ord("A") + len(sym) - 26))
+            eq = ("".join(sym[ix] for ix in terms[i]) + "," + "".join(sym[ix] for ix in terms[j]) + "->"
+                  + "".join(sym[ix] for ix in keep))
+            new = np.einsum(eq, data[i], data[j])
+            for k in (i, j):
+                for ix in terms[k]:
+                    where[ix].discard(k)
+                del terms[k], data[k]
+            terms[nxt], data[nxt] = tuple(keep), new
+            for ix in keep:
+                where.setdefault(ix, set()).add(nxt)
+            nxt += 1
+            changed = True
+        if not changed:
+            break
+    order = sorted(terms)
+    new_inputs = [terms[i] for i in order]
+    used = {ix for t in new_inputs for ix in t} | set(output)
+    return new_inputs, output, {ix: d for ix, d in size_dict.items() if ix in used}, [data[i] for i in order]

@@ -40,10 +40,19 @@ def main(which):
     vpath = os.path.join(GOLDEN_DIR, "circuits_values.npz")
     vals = dict(np.load(vpath)) if os.path.exists(vpath) else {}
     for name in which:
-        qsim = f"/root/reference/examples/circuit_n53_{name}_s0_e0_pABCDCDAB.qsim"
+        # "m10s" / "m12s": the rank-simplified network (what the reference notebooks contract:
+        # 164 tensors for m10, Quantum Circuit Example Old.ipynb:143)
+        simplified = name.endswith("s")
+        base = name[:-1] if simplified else name
+        qsim = f"/root/reference/examples/circuit_n53_{base}_s0_e0_pABCDCDAB.qsim"
         inputs, output, size_dict, arrays = amplitude_network(qsim)
+        if simplified:
+            from cotengra_b200.circuits import rank_simplify
+
+            inputs, output, size_dict, arrays = rank_simplify(inputs, output, size_dict, arrays)
+            print(name, "rank-simplified to", len(inputs), "tensors", len(size_dict), "indices", flush=True)
         t0 = time.time()
-        if name == "m10":
+        if base == "m10":
             tree = search(inputs, output, size_dict, 32, 240)
         else:
             tree = search(inputs, output, size_dict, 48, 600)
@@ -55,11 +64,11 @@ def main(which):
                "contract_stats": {k: int(v) for k, v in tree.contract_stats().items()},
                "nslices": int(tree.nslices), "peak_size": int(tree.peak_size())}
         # golden value(s) from the reference's numpy path
-        if name == "m10":
+        if base == "m10":
             t0 = time.time()
             val = tree.contract(arrays)
-            print("m10 reference contraction", round(time.time() - t0, 1), "s value", val, flush=True)
-            vals["m10_amplitude"] = np.asarray(val)
+            print(name, "reference contraction", round(time.time() - t0, 1), "s value", val, flush=True)
+            vals[f"{name}_amplitude"] = np.asarray(val)
         # a further-sliced copy whose single slices are cheap on the CPU
         small = tree.copy()
         small.slice_(target_size=2**22)
@@ -70,6 +79,12 @@ def main(which):
         recs[name] = rec
         json.dump(recs, open(path, "w"))
         np.savez_compressed(vpath, **vals)
+        # the gate tensors themselves (flattened, input order), so that the fixture is usable
+        # where the .qsim files are not (the GPU box)
+        apath = os.path.join(GOLDEN_DIR, "circuits_arrays.npz")
+        arrs = dict(np.load(apath)) if os.path.exists(apath) else {}
+        arrs[f"{name}_arrays_flat"] = np.concatenate([np.asarray(a, dtype=np.complex128).reshape(-1) for a in arrays])
+        np.savez_compressed(apath, **arrs)
         print(name, "written", flush=True)
 
 

@@ -1,6 +1,6 @@
 """Per-node timing of one slice of the Sycamore-m20 Appendix-B tree (dev tool).
 
-usage: python scripts/gpu_profile_slice.py [dtype] [width_log2] [--nodmma]
+usage: python scripts/gpu_profile_slice.py [dtype] [width_log2] [--nodmma] [--nofuse]
 Writes gpurun_out/nodes_<dtype>_w<width>.csv and prints a summary."""
 import json
 import os
@@ -19,17 +19,19 @@ from tests.slicing_util import slice_to_width
 dtype = sys.argv[1] if len(sys.argv) > 1 else "complex128"
 wlog = int(sys.argv[2]) if len(sys.argv) > 2 else 30
 nodmma = "--nodmma" in sys.argv
+nofuse = "--nofuse" in sys.argv
 rec = next(r for r in load_json("sycamore_m20.json") if r["name"] == "sycamore_m20_appxB")
 spec = cb.TreeSpec(rec["inputs"], rec["output"], rec["size_dict"], rec["path"], decode_sliced(rec["sliced"]))
 if wlog < 30:
     spec = slice_to_width(spec, 2**wlog)
 print("peaks", _lib.probe_fp64_peaks(), flush=True)
 t0 = time.time()
-ex = cb.TreeExecutor(spec, dtype=dtype, allow_dmma=not nodmma)
+ex = cb.TreeExecutor(spec, dtype=dtype, allow_dmma=not nodmma, fuse=not nofuse)
+print("fusion", {k: v for k, v in ex.fusion.items()}, flush=True)
 plan = ex.plan
 print(f"plan built in {time.time()-t0:.1f}s  ws={plan.workspace_bytes/2**30:.2f} GiB persistent={plan.persistent_bytes/2**20:.1f} MiB "
       f"macs/slice={plan.macs_per_slice:.4g} elements/slice={plan.elements_per_slice:.4g}", flush=True)
-arrays = make_arrays(spec.shapes(), dtype, seed=0)
+arrays = make_arrays(spec.shapes(), dtype, seed=0, scale=0.65)
 dev = [torch.from_numpy(a).cuda() for a in arrays]
 for _ in range(2):
     out = ex.contract_device(dev, begin=0, step=1, count=1)
@@ -41,7 +43,7 @@ out = ex.contract_device(dev, begin=1, step=1, count=reps)
 e1.record()
 torch.cuda.synchronize()
 ms = e0.elapsed_time(e1) / reps
-flops = 8 * plan.macs_per_slice
+flops = 8 * ex.reference_work[0]  # the reference tree's work
 es = plan.esize
 print(f"slice: {ms:.2f} ms  {flops/ms/1e9:.2f} TFLOP/s  ideal-traffic {plan.elements_per_slice*es/ms/1e6:.1f} GB/s  value={out.cpu().numpy()}", flush=True)
 plan.profile(True)
@@ -62,7 +64,7 @@ for nd, t in zip(plan.nodes, times):
 rows.sort(key=lambda r: -r["ms"])
 tot = sum(r["ms"] for r in rows)
 os.makedirs("gpurun_out", exist_ok=True)
-tag = f"{dtype}_w{wlog}{'_nodmma' if nodmma else ''}"
+tag = f"{dtype}_w{wlog}{'_nodmma' if nodmma else ''}{'_nofuse' if nofuse else ''}"
 with open(f"gpurun_out/nodes_{tag}.csv", "w") as f:
     f.write("ms,share,M,N,K,variant,splitk,tiles,MTa,NTa,KTa,tflops,gbs\n")
     for r in rows:

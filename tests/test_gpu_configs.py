@@ -76,6 +76,23 @@ def test_config3_sycamore_m10_amplitude():
         assert rel_err(g, vals[f"m10_small_slice{i}"]) < 1e-10
 
 
+def test_config3_sycamore_m10_simplified_network():
+    """Config 3 as the reference notebooks run it: the rank-simplified m10 network (164 tensors,
+    `Quantum Circuit Example Old.ipynb:143`; cotengra_b200.circuits.rank_simplify), tree searched
+    by the unmodified reference; same amplitude as the 1764-tensor network."""
+    rec, spec, arrays = _circuit("m10s")
+    assert spec.N == 164
+    vals = load_npz("circuits_values.npz")
+    want = vals["m10s_amplitude"]
+    assert rel_err(want, vals["m10_amplitude"]) < 1e-10  # the reference agrees with itself
+    got = cb.contract_tree(spec, arrays)
+    assert rel_err(got, want) < 1e-10
+    small = cb.TreeSpec.from_dict(rec["small_spec"])
+    for i in (0, 3):
+        g = cb.contract_tree(small, arrays, slice_ids=(i, 1, 1))
+        assert rel_err(g, vals[f"m10s_small_slice{i}"]) < 1e-10
+
+
 def test_config4_sycamore_m12_sliced():
     rec, spec, arrays = _circuit("m12")
     vals = load_npz("circuits_values.npz")
