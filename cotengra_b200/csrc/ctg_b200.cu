@@ -151,12 +151,17 @@ int launch_rowstream(const int64_t* h, const int64_t* d, const void* A, const vo
   const T* a = (const T*)A;
   const T* b = (const T*)B;
   T* c = (T*)C;
-  if (N <= 4 && K <= 4)
-    rowstream_kernel<T, 4, 4, true><<<(unsigned)blocks, 256, 0, st>>>(d, a, b, c);
-  else if (N <= 2)  // (B from shared memory: in registers it costs 154 registers = one block / SM)
-    rowstream_kernel<T, 2, 8, sizeof(T) < 16><<<(unsigned)blocks, 256, 0, st>>>(d, a, b, c);
-  else
-    rowstream_kernel<T, 8, 8, false><<<(unsigned)blocks, 256, 0, st>>>(d, a, b, c);
+  const bool strip = h[W_SCALE_A] != 0;  // fused strip_exponent: separate instantiations
+  if (N <= 4 && K <= 4) {
+    if (strip) rowstream_kernel<T, 4, 4, true, true><<<(unsigned)blocks, 256, 0, st>>>(d, a, b, c);
+    else rowstream_kernel<T, 4, 4, true><<<(unsigned)blocks, 256, 0, st>>>(d, a, b, c);
+  } else if (N <= 2) {  // (B from shared memory: in registers it costs 154 registers = one block / SM)
+    if (strip) rowstream_kernel<T, 2, 8, sizeof(T) < 16, true><<<(unsigned)blocks, 256, 0, st>>>(d, a, b, c);
+    else rowstream_kernel<T, 2, 8, sizeof(T) < 16><<<(unsigned)blocks, 256, 0, st>>>(d, a, b, c);
+  } else {
+    if (strip) rowstream_kernel<T, 8, 8, false, true><<<(unsigned)blocks, 256, 0, st>>>(d, a, b, c);
+    else rowstream_kernel<T, 8, 8, false><<<(unsigned)blocks, 256, 0, st>>>(d, a, b, c);
+  }
   g_launches.fetch_add(1, std::memory_order_relaxed);
   CUDA_TRY(cudaGetLastError());
   return CTGB_OK;
@@ -192,6 +197,30 @@ int launch_dotstream(const int64_t* h, const int64_t* d, const void* A, const vo
   return CTGB_OK;
 }
 
+int launch_dotdmma(const int64_t* h, const int64_t* d, const void* A, const void* B, void* C, cudaStream_t st) {
+  DevInfo& di = devinfo();
+  if (!di.ok) return fail(CTGB_E_CUDA, "no CUDA device");
+  if (h[W_DTYPE] != CTGB_C128 || h[W_MTA] > 32 || h[W_NTA] > 32 || h[W_TILES_M] != 1 || h[W_TILES_N] != 1 ||
+      h[W_TILES_B] != 1 || h[W_KTA] != DD_KT || h[W_NGK] > 64 || h[W_STEPS_K] >= (1ll << 31) || h[W_PGM] >= 0 ||
+      h[W_PGN] >= 0 || (h[W_PGK] >= 0 && (h[W_KFULL] % h[W_KTEXT]) != 0))
+    return fail(CTGB_E_VALUE, "descriptor does not fit the DMMA dot kernel");
+  if (h[W_STEPS_K] == 0) return CTGB_OK;
+  if (!(h[W_FLAGS] & 1)) {
+    const long long celems = h[W_MTA] * h[W_NTA];
+    if (h[W_CELEMS] != celems) return fail(CTGB_E_VALUE, "DMMA dot into a strided C needs accumulate");
+    CUDA_TRY(cudaMemsetAsync(C, 0, (size_t)celems * sizeof(double2), st));
+  }
+  unsigned long long blocks = (unsigned long long)h[W_STEPS_K];
+  if (blocks > (unsigned long long)di.sms) blocks = (unsigned long long)di.sms;  // one block per SM, one wave
+  if (h[W_MTA] <= 16 && h[W_NTA] <= 16)
+    dotdmma_kernel<2, 2><<<(unsigned)blocks, DD_WARPS * 32, 0, st>>>(d, (const double2*)A, (const double2*)B, (double2*)C);
+  else
+    dotdmma_kernel<4, 4><<<(unsigned)blocks, DD_WARPS * 32, 0, st>>>(d, (const double2*)A, (const double2*)B, (double2*)C);
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  CUDA_TRY(cudaGetLastError());
+  return CTGB_OK;
+}
+
 int launch_dmmastream(const int64_t* h, const int64_t* d, const void* A, const void* B, void* C, cudaStream_t st) {
   DevInfo& di = devinfo();
   if (!di.ok) return fail(CTGB_E_CUDA, "no CUDA device");
@@ -206,10 +235,15 @@ int launch_dmmastream(const int64_t* h, const int64_t* d, const void* A, const v
   unsigned long long blocks = (M + 127) / 128;  // 4 warps x 32 rows per block and pass
   const unsigned long long cap = (unsigned long long)di.sms * 12;
   if (blocks > cap) blocks = cap;
-  if (N <= 16)
-    dmmastream_kernel<2><<<(unsigned)blocks, 128, 0, st>>>(d, (const double2*)A, (const double2*)B, (double2*)C);
-  else
-    dmmastream_kernel<4><<<(unsigned)blocks, 128, 0, st>>>(d, (const double2*)A, (const double2*)B, (double2*)C);
+  const bool strip = h[W_SCALE_A] != 0;  // fused strip_exponent: separate instantiations
+  const double2 *a = (const double2*)A, *b = (const double2*)B;
+  if (N <= 16) {
+    if (strip) dmmastream_kernel<2, true><<<(unsigned)blocks, 128, 0, st>>>(d, a, b, (double2*)C);
+    else dmmastream_kernel<2><<<(unsigned)blocks, 128, 0, st>>>(d, a, b, (double2*)C);
+  } else {
+    if (strip) dmmastream_kernel<4, true><<<(unsigned)blocks, 128, 0, st>>>(d, a, b, (double2*)C);
+    else dmmastream_kernel<4><<<(unsigned)blocks, 128, 0, st>>>(d, a, b, (double2*)C);
+  }
   g_launches.fetch_add(1, std::memory_order_relaxed);
   CUDA_TRY(cudaGetLastError());
   return CTGB_OK;
@@ -293,6 +327,7 @@ int launch_gett_typed(const int64_t* h, const int64_t* d, const void* A, const v
   if (variant == VAR_ROWSTREAM) return launch_rowstream<T>(h, d, A, B, C, st);
   if (variant == VAR_DMMASTREAM) return launch_dmmastream(h, d, A, B, C, st);
   if (variant == VAR_DOTSTREAM || variant == VAR_DOTSTREAM4) return launch_dotstream<T>(h, d, A, B, C, st);
+  if (variant == VAR_DOTDMMA) return launch_dotdmma(h, d, A, B, C, st);
   if constexpr (std::is_same<T, float2>::value) {
     if (variant == VAR_TC05_128x64) return launch_tc05<64>(h, d, A, B, C, st);
     if (variant == VAR_TC05_128x32) return launch_tc05<32>(h, d, A, B, C, st);
@@ -374,42 +409,42 @@ unsigned flat_grid(long long n) {
   return (unsigned)b;
 }
 
+// max|C| of a node whose own epilogue cannot measure it (split-K / block partial sums)
 template <typename T>
-int strip_typed(void* p, long long n, unsigned long long* slot, double* exponent, cudaStream_t st) {
-  zero_slot_kernel<<<1, 1, 0, st>>>(slot);
+int absmax_typed(const void* p, long long n, unsigned long long* slot, cudaStream_t st) {
   absmax_kernel<T><<<flat_grid(n), 256, 0, st>>>((const T*)p, n, slot);
-  strip_kernel<T><<<flat_grid(n), 256, 0, st>>>((T*)p, n, slot, exponent);
-  g_launches.fetch_add(3, std::memory_order_relaxed);
+  g_launches.fetch_add(1, std::memory_order_relaxed);
   CUDA_TRY(cudaGetLastError());
   return CTGB_OK;
 }
-int strip(int dtype, void* p, long long n, unsigned long long* slot, double* exponent, cudaStream_t st) {
+int absmax_into(int dtype, const void* p, long long n, unsigned long long* slot, cudaStream_t st) {
   switch (dtype) {
-    case CTGB_F32: return strip_typed<float>(p, n, slot, exponent, st);
-    case CTGB_F64: return strip_typed<double>(p, n, slot, exponent, st);
-    case CTGB_C64: return strip_typed<float2>(p, n, slot, exponent, st);
-    case CTGB_C128: return strip_typed<double2>(p, n, slot, exponent, st);
+    case CTGB_F32: return absmax_typed<float>(p, n, slot, st);
+    case CTGB_F64: return absmax_typed<double>(p, n, slot, st);
+    case CTGB_C64: return absmax_typed<float2>(p, n, slot, st);
+    case CTGB_C128: return absmax_typed<double2>(p, n, slot, st);
   }
   return fail(CTGB_E_VALUE, "bad dtype");
 }
 
 template <typename T>
 int accum_stripped_typed(const int64_t* dchunk, const int64_t* hchunk, void* out, void* chunk, long long out_elems,
-                         const void* m, double* E, const double* es, cudaStream_t st) {
+                         const void* m, double* E, const double* es, const double* froot, cudaStream_t st) {
   rescale_out_kernel<T><<<flat_grid(out_elems), 256, 0, st>>>((T*)out, out_elems, E, es);
-  add_chunk_kernel<T><<<flat_grid(hchunk[S_OUT_ELEMS]), 256, 0, st>>>(dchunk, (T*)chunk, (const T*)m, E, es);
+  add_chunk_kernel<T><<<flat_grid(hchunk[S_OUT_ELEMS]), 256, 0, st>>>(dchunk, (T*)chunk, (const T*)m, E, es, froot);
   commit_exponent_kernel<<<1, 1, 0, st>>>(E, es);
   g_launches.fetch_add(3, std::memory_order_relaxed);
   CUDA_TRY(cudaGetLastError());
   return CTGB_OK;
 }
 int accum_stripped(int dtype, const int64_t* dchunk, const int64_t* hchunk, void* out, void* chunk,
-                   long long out_elems, const void* m, double* E, const double* es, cudaStream_t st) {
+                   long long out_elems, const void* m, double* E, const double* es, const double* froot,
+                   cudaStream_t st) {
   switch (dtype) {
-    case CTGB_F32: return accum_stripped_typed<float>(dchunk, hchunk, out, chunk, out_elems, m, E, es, st);
-    case CTGB_F64: return accum_stripped_typed<double>(dchunk, hchunk, out, chunk, out_elems, m, E, es, st);
-    case CTGB_C64: return accum_stripped_typed<float2>(dchunk, hchunk, out, chunk, out_elems, m, E, es, st);
-    case CTGB_C128: return accum_stripped_typed<double2>(dchunk, hchunk, out, chunk, out_elems, m, E, es, st);
+    case CTGB_F32: return accum_stripped_typed<float>(dchunk, hchunk, out, chunk, out_elems, m, E, es, froot, st);
+    case CTGB_F64: return accum_stripped_typed<double>(dchunk, hchunk, out, chunk, out_elems, m, E, es, froot, st);
+    case CTGB_C64: return accum_stripped_typed<float2>(dchunk, hchunk, out, chunk, out_elems, m, E, es, froot, st);
+    case CTGB_C128: return accum_stripped_typed<double2>(dchunk, hchunk, out, chunk, out_elems, m, E, es, froot, st);
   }
   return fail(CTGB_E_VALUE, "bad dtype");
 }
@@ -430,6 +465,7 @@ struct ctgb_plan {
     int kind, a, b, c, invariant, is_root;
     size_t desc_off;  // word offset into descs
     int64_t c_elems;  // dense elements of the result (strip_exponent)
+    int measure_after = 0;  // strip_exponent: max|C| needs its own pass (split-K / block partial sums)
   };
   std::vector<Tensor> tensors;
   std::vector<Node> nodes;
@@ -439,8 +475,13 @@ struct ctgb_plan {
   int64_t out_elements = 0, workspace_bytes = 0, persistent_bytes = 0;
   int strip_exponent = 0;
   int64_t launches_per_slice = 0;
-  // strip_exponent scratch (device): [0] factor slot, [1] slice exponent, [2] invariant exponent
+  // strip_exponent scratch (device): [1] slice exponent, [2] invariant exponent
   double* d_scalars = nullptr;
+  // fused strip_exponent: one factor slot per tensor (1.0 for inputs and single-operand results,
+  // max|C| for pairwise results) and the slots to reset / sum per pass
+  double* d_factors = nullptr;
+  int* d_slot_lists = nullptr;  // [variant slots..., invariant slots...]
+  int n_var_slots = 0, n_inv_slots = 0;
   // chunk descriptor for stripped accumulation (host + device), built at create
   std::vector<int64_t> chunk_desc;
   int64_t* d_chunk_desc = nullptr;
@@ -581,8 +622,14 @@ int ctgb_plan_create(const ctgb_plan_desc* pd, ctgb_plan** out) {
     q.desc_off = p->descs.size();
     p->descs.insert(p->descs.end(), n.desc, n.desc + words);
     q.c_elems = p->tensors[n.c].nbytes / (int64_t)elem_size(pd->dtype);
-    if (!n.invariant) per_slice += 1 + (pd->strip_exponent ? 3 : 0);
+    if (pd->strip_exponent && n.kind == 0) {
+      const int64_t* w = n.desc;
+      q.measure_after = w[W_SPLITK] > 1 || w[W_VARIANT] == VAR_DOTSTREAM || w[W_VARIANT] == VAR_DOTSTREAM4 ||
+                        w[W_VARIANT] == VAR_DOTDMMA;
+    }
+    if (!n.invariant) per_slice += 1 + q.measure_after;
   }
+  if (pd->strip_exponent) per_slice += 5;  // reset slots, sum of logs, rescale/add/commit
   p->launches_per_slice = per_slice;
   p->radix.assign(pd->slice_radix, pd->slice_radix + pd->n_sliced);
   p->project.assign(pd->slice_project, pd->slice_project + pd->n_sliced);
@@ -601,6 +648,30 @@ int ctgb_plan_create(const ctgb_plan_desc* pd, ctgb_plan** out) {
     e = cudaMemcpy(p->d_descs, p->descs.data(), p->descs.size() * sizeof(int64_t), cudaMemcpyHostToDevice);
   if (e == cudaSuccess) e = cudaMalloc((void**)&p->d_scalars, 8 * sizeof(double));
   if (e == cudaSuccess) e = cudaMemset(p->d_scalars, 0, 8 * sizeof(double));
+  if (e == cudaSuccess && p->strip_exponent) {
+    // factor slots + the per-node pointers into them (patched into the plan's descriptors)
+    const size_t nt = p->tensors.size();
+    std::vector<double> ones(nt + 1, 1.0);
+    e = cudaMalloc((void**)&p->d_factors, (nt + 1) * sizeof(double));
+    if (e == cudaSuccess) e = cudaMemcpy(p->d_factors, ones.data(), (nt + 1) * sizeof(double), cudaMemcpyHostToDevice);
+    std::vector<int> var_slots, inv_slots;
+    for (auto& n : p->nodes) {
+      if (n.kind != 0) continue;
+      int64_t* w = p->descs.data() + n.desc_off;
+      w[W_SCALE_A] = (int64_t)(uintptr_t)(p->d_factors + n.a);
+      w[W_SCALE_B] = (int64_t)(uintptr_t)(p->d_factors + n.b);
+      w[W_FACTOR_C] = n.measure_after ? 0 : (int64_t)(uintptr_t)(p->d_factors + n.c);
+      (n.invariant ? inv_slots : var_slots).push_back(n.c);
+    }
+    p->n_var_slots = (int)var_slots.size();
+    p->n_inv_slots = (int)inv_slots.size();
+    var_slots.insert(var_slots.end(), inv_slots.begin(), inv_slots.end());
+    if (e == cudaSuccess) e = cudaMalloc((void**)&p->d_slot_lists, (var_slots.size() + 1) * sizeof(int));
+    if (e == cudaSuccess && !var_slots.empty())
+      e = cudaMemcpy(p->d_slot_lists, var_slots.data(), var_slots.size() * sizeof(int), cudaMemcpyHostToDevice);
+    if (e == cudaSuccess)
+      e = cudaMemcpy(p->d_descs, p->descs.data(), p->descs.size() * sizeof(int64_t), cudaMemcpyHostToDevice);
+  }
   if (e != cudaSuccess) {
     std::string msg = cudaGetErrorString(e);
     ctgb_plan_destroy(p);
@@ -645,6 +716,8 @@ void ctgb_plan_destroy(ctgb_plan* p) {
   for (auto e : p->ev1) cudaEventDestroy(e);
   if (p->d_descs) cudaFree(p->d_descs);
   if (p->d_scalars) cudaFree(p->d_scalars);
+  if (p->d_factors) cudaFree(p->d_factors);
+  if (p->d_slot_lists) cudaFree(p->d_slot_lists);
   if (p->d_chunk_desc) cudaFree(p->d_chunk_desc);
   if (p->h_stage) cudaFreeHost(p->h_stage);
   delete p;
@@ -680,7 +753,6 @@ int ctgb_plan_execute(ctgb_plan* p, const void* const* inputs, void* out, double
   const int ns = (int)p->radix.size();
   std::vector<int64_t> digits(ns, 0);
 
-  unsigned long long* d_slot = (unsigned long long*)(p->d_scalars + 0);
   double* d_slice_exp = p->d_scalars + 1;
   double* d_inv_exp = p->d_scalars + 2;
 
@@ -698,7 +770,7 @@ int ctgb_plan_execute(ctgb_plan* p, const void* const* inputs, void* out, double
     }
   };
 
-  auto run_nodes = [&](bool invariant_pass, int64_t out_off, double* exp_acc) -> int {
+  auto run_nodes = [&](bool invariant_pass, int64_t out_off) -> int {
     for (size_t ni = 0; ni < p->nodes.size(); ++ni) {
       const auto& n = p->nodes[ni];
       if ((n.invariant != 0) != invariant_pass) continue;
@@ -715,10 +787,12 @@ int ctgb_plan_execute(ctgb_plan* p, const void* const* inputs, void* out, double
         rc = launch_single(h, d, A, C, st);
       }
       if (rc) return rc;
-      // contract.py:816-829 strips after every *pairwise* node (single-operand
-      // preprocessing steps `continue` before reaching it, :792-796)
-      if (p->strip_exponent && n.kind == 0) {
-        rc = strip(p->dtype, C, n.c_elems, d_slot, exp_acc, st);
+      // contract.py:816-829 strips after every *pairwise* node (single-operand preprocessing
+      // steps `continue` before reaching it, :792-796).  The kernels do it in their epilogues
+      // (scale by the operands' factors, record max|C|: gett_kernels.cuh StripCtx); only nodes
+      // that add partial sums atomically need max|C| measured in a pass of its own.
+      if (p->strip_exponent && n.kind == 0 && n.measure_after) {
+        rc = absmax_into(p->dtype, C, n.c_elems, (unsigned long long*)(p->d_factors + n.c), st);
         if (rc) return rc;
       }
       if (p->profile) cudaEventRecord(p->ev1[ni], st);
@@ -729,13 +803,19 @@ int ctgb_plan_execute(ctgb_plan* p, const void* const* inputs, void* out, double
   // slice-invariant subtrees: once per execute call, kept in the persistent arena
   bool any_inv = false;
   for (const auto& n : p->nodes) any_inv |= n.invariant != 0;
-  if (p->strip_exponent) {
-    set_double_kernel<<<1, 1, 0, st>>>(d_inv_exp, 0.0);
+  if (p->strip_exponent && p->n_inv_slots > 0) {
+    reset_slots_kernel<<<1, 256, 0, st>>>(p->d_factors, p->d_slot_lists + p->n_var_slots, p->n_inv_slots);
     g_launches.fetch_add(1, std::memory_order_relaxed);
   }
   if (any_inv) {
-    int rc = run_nodes(true, 0, d_inv_exp);
+    int rc = run_nodes(true, 0);
     if (rc) return rc;
+  }
+  if (p->strip_exponent) {
+    // exponent of the slice-invariant part: sum of log10(factor) over the hoisted pairwise nodes
+    sum_log_kernel<<<1, 256, 0, st>>>(p->d_factors, p->d_slot_lists + p->n_var_slots, p->n_inv_slots, d_inv_exp,
+                                      nullptr);
+    g_launches.fetch_add(1, std::memory_order_relaxed);
   }
 
   for (int64_t k = 0; k < slice_count; ++k) {
@@ -757,13 +837,15 @@ int ctgb_plan_execute(ctgb_plan* p, const void* const* inputs, void* out, double
     }
     int64_t out_off = 0;
     for (int j = 0; j < ns; ++j) out_off += digits[j] * p->out_stride[j];
-    if (p->strip_exponent) {
-      copy_double_kernel<<<1, 1, 0, st>>>(d_slice_exp, d_inv_exp);
+    if (p->strip_exponent && p->n_var_slots > 0) {
+      reset_slots_kernel<<<1, 256, 0, st>>>(p->d_factors, p->d_slot_lists, p->n_var_slots);
       g_launches.fetch_add(1, std::memory_order_relaxed);
     }
-    int rc = run_nodes(false, out_off, d_slice_exp);
+    int rc = run_nodes(false, out_off);
     if (rc) return rc;
     if (p->strip_exponent) {
+      sum_log_kernel<<<1, 256, 0, st>>>(p->d_factors, p->d_slot_lists, p->n_var_slots, d_slice_exp, d_inv_exp);
+      g_launches.fetch_add(1, std::memory_order_relaxed);
       // the root wrote a dense mantissa into its workspace slot; fold it into the
       // output against the running exponent (core.py:163-170, 3856-3861)
       const ctgb_plan::Node* root = nullptr;
@@ -771,8 +853,10 @@ int ctgb_plan_execute(ctgb_plan* p, const void* const* inputs, void* out, double
         if (n.is_root) root = &n;
       if (!root) return fail(CTGB_E_VALUE, "plan has no root node");
       char* m = resolve(root->c, 0);
+      // (the stored root is the raw product: its own factor divides it here)
+      const double* froot = root->kind == 0 ? p->d_factors + root->c : nullptr;
       rc = accum_stripped(p->dtype, p->d_chunk_desc, p->chunk_desc.data(), out, (char*)out + out_off * (int64_t)es,
-                          p->out_elements, m, exponent_dev, d_slice_exp, st);
+                          p->out_elements, m, exponent_dev, d_slice_exp, froot, st);
       if (rc) return rc;
     }
   }

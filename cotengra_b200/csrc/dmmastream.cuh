@@ -16,7 +16,7 @@ constexpr int DS_KMAX = 32;
 
 // NJ = column fragments (N <= 8*NJ).  128 threads x 3 blocks (NJ = 2: <= 170 registers) or x 2 blocks
 // (NJ = 4: 128 accumulator registers), 16 loads in flight per lane
-template <int NJ>
+template <int NJ, bool STRIP = false>
 __global__ void __launch_bounds__(128, NJ <= 2 ? 3 : 2)
 dmmastream_kernel(const int64_t* __restrict__ D, const double2* __restrict__ A, const double2* __restrict__ B,
                   double2* __restrict__ C) {
@@ -84,6 +84,8 @@ dmmastream_kernel(const int64_t* __restrict__ D, const double2* __restrict__ A, 
   }
   __syncthreads();
 
+  [[maybe_unused]] StripCtx sctx;  // fused strip_exponent: its own instantiation (register-bound loop)
+  if constexpr (STRIP) sctx = strip_begin(D);
   const int frow = lane >> 2, fk = lane & 3, fc = (lane & 3) * 2;
   const int n8s = (N + 7) >> 3;       // column fragments in use
   const int kchunks = (K + 15) >> 4;  // chunks of 16 k (4 k4-steps each)
@@ -175,7 +177,11 @@ dmmastream_kernel(const int64_t* __restrict__ D, const double2* __restrict__ A, 
       for (int j = 0; j < NJ; ++j) {
         const int c = j * 8 + fc;
         if (c >= N) continue;
-        const double2 v0 = make_double2(re[i][j][0], im[i][j][0]), v1 = make_double2(re[i][j][1], im[i][j][1]);
+        double2 v0 = make_double2(re[i][j][0], im[i][j][0]), v1 = make_double2(re[i][j][1], im[i][j][1]);
+        if constexpr (STRIP) {
+          v0 = strip_apply(sctx, v0);
+          if (c + 1 < N) v1 = strip_apply(sctx, v1);
+        }
         if (pair_ok) {
           store_pair_of(crow + s_cnoff[c], v0, v1);
         } else {
@@ -189,4 +195,5 @@ dmmastream_kernel(const int64_t* __restrict__ D, const double2* __restrict__ A, 
       }
     }
   }
+  if constexpr (STRIP) strip_end(sctx);
 }

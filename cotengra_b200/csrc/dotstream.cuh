@@ -17,8 +17,9 @@ constexpr int DOT_KT = 2048, DOT_THREADS = 256, DOT_U = DOT_KT / DOT_THREADS;
 // the same stream with a small kept space on both operands (M, N <= 4): the last small tensor
 // of a stem peeled over the final inner product (cotengra_b200/fusion.py),
 //   R[m, n] = sum_k A[k, m] * B[k, n],
-// 16 accumulators per thread, 2 k per thread and tile (8 + 8 loads in flight)
-constexpr int DOT4_MN = 4, DOT4_U = 2, DOT4_KT = DOT4_U * DOT_THREADS;
+// 16 accumulators per thread, 4 k per thread and tile (16 + 16 loads in flight: 128 KB per SM,
+// what the 1x1 kernel needs for 6.9 TB/s; with 2 k it stopped at 5.6 TB/s)
+constexpr int DOT4_MN = 4, DOT4_U = 4, DOT4_KT = DOT4_U * DOT_THREADS;
 
 template <typename T, int MT, int NT, int U>
 __global__ void __launch_bounds__(DOT_THREADS, (MT * NT > 1) ? 1 : 2)
@@ -134,6 +135,8 @@ dotstream_kernel(const int64_t* __restrict__ D, const T* __restrict__ A, const T
     if (i < MTa && c < NTa) {
       T v = s_part[0][tid];
       for (int w = 1; w < DOT_THREADS / 32; ++w) v = add_of(v, s_part[w][tid]);
+      StripCtx sctx = strip_begin(D);  // strip_exponent: partial sums are only scaled here
+      if (sctx.scale) v = strip_apply(sctx, v);
       long long oc = 0;
       unsigned e = (unsigned)i;
       for (int d = 0; d < (int)D[W_NTM]; ++d) {

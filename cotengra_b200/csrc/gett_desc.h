@@ -42,6 +42,11 @@ enum : int {
   W_CELEMS = 33,       // elements of a dense C (memset before split-K atomics); 0: strided C
   W_RUNA = 34,         // tcgen05: elements of the contiguous runs the A tile is made of (flags bit6)
   W_LBOPAD = 35,       // tcgen05: chunk-stride padding of the A' images, x16 bytes (bank spreading)
+  // fused strip_exponent (contract.py:816-829), patched into the plan's device copy of the
+  // descriptor by ctgb_plan_create; 0 = off.  Device addresses of doubles:
+  W_SCALE_A = 36,      //   max|A| of operand A as stored (A is a lazily-normalised intermediate) or 1.0
+  W_SCALE_B = 37,      //   same for B; the epilogue multiplies by 1/(fA*fB)
+  W_FACTOR_C = 38,     //   slot receiving max|C| of what this launch stores (atomicMax of the double's bits)
   W_HDR = 40,
   // arrays
   OFF_TM = W_HDR,                 // MAX_T x (ext, sA, sC)
@@ -76,7 +81,8 @@ enum : int {
   VAR_DMMA3M_256x16 = 13,
   VAR_DOTSTREAM = 15,      // M = N = 1: the final inner product, operands straight from global memory
   VAR_DMMASTREAM = 14,     // complex128, 8 < N <= 16, K <= 32: DMMA fragments straight from global memory
-  VAR_DOTSTREAM4 = 16      // M, N <= 4 over a huge contracted range: a peeled stem tail times the other stem
+  VAR_DOTSTREAM4 = 16,     // M, N <= 4 over a huge contracted range: a peeled stem tail times the other stem
+  VAR_DOTDMMA = 17         // complex128, M, N <= 32 over a huge contracted range: the same on DMMA fragments
 };
 
 // ---- single-operand descriptor (cotengra/contract.py:332-361) -------------

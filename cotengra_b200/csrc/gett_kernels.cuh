@@ -81,6 +81,79 @@ __device__ __forceinline__ double2 shfl_down_of(double2 v, int d) {
   return make_double2(__shfl_down_sync(0xffffffffu, v.x, d), __shfl_down_sync(0xffffffffu, v.y, d));
 }
 
+// ------------------------------------------------------------------ fused strip_exponent
+// contract.py:816-829 normalises every pairwise result by its largest magnitude and adds the
+// log10 of that factor to a running exponent.  Done literally that is two extra passes over
+// every intermediate (max, then divide).  Here the division is LAZY: a node stores its raw
+// product and records factor = max|C| in a slot; whoever consumes C multiplies its own
+// accumulators by 1/(factor_A * factor_B) in the epilogue -- the same numbers the reference
+// forms, (A/fA)(B/fB), since the product is bilinear -- and the exponent is the sum of
+// log10(factor) over the nodes, formed once per slice.
+struct StripCtx {
+  double sa, sb;            // 1/fA, 1/fB (0 when the operand is identically zero: check_zero)
+  double run;               // largest |value| this thread has stored
+  unsigned long long* fc;   // factor slot of C (nullptr: the caller measures C separately)
+  bool scale;
+};
+__device__ __forceinline__ StripCtx strip_begin(const int64_t* __restrict__ D) {
+  StripCtx c;
+  const double* pa = reinterpret_cast<const double*>(D[W_SCALE_A]);
+  const double* pb = reinterpret_cast<const double*>(D[W_SCALE_B]);
+  c.scale = pa != nullptr;
+  c.fc = reinterpret_cast<unsigned long long*>(D[W_FACTOR_C]);
+  c.run = 0.0;
+  c.sa = c.sb = 1.0;
+  if (c.scale) {
+    const double fa = *pa, fb = *pb;
+    c.sa = fa != 0.0 ? 1.0 / fa : 0.0;
+    c.sb = fb != 0.0 ? 1.0 / fb : 0.0;
+  }
+  return c;
+}
+__device__ __forceinline__ void strip_track(StripCtx& c, double re, double im) {
+  // max of hypot(re, im) without a hypot per element: only candidates that can beat the
+  // running maximum pay for it (no squaring: |v| down to the denormals keeps its value)
+  // (|re| + |im| >= hypot, and it is NaN when either part is: NaN is sticky, as in numpy's max)
+  if (c.run != c.run) return;
+  const double a = fabs(re) + fabs(im);
+  if (!(a <= c.run)) {
+    const double h = hypot(re, im);
+    c.run = (h != h) ? h : fmax(c.run, h);
+  }
+}
+__device__ __forceinline__ float strip_apply(StripCtx& c, float v) {
+  const float r = (float)((double)v * c.sa * c.sb);
+  strip_track(c, (double)r, 0.0);
+  return r;
+}
+__device__ __forceinline__ double strip_apply(StripCtx& c, double v) {
+  const double r = v * c.sa * c.sb;
+  strip_track(c, r, 0.0);
+  return r;
+}
+__device__ __forceinline__ float2 strip_apply(StripCtx& c, float2 v) {
+  const float2 r = make_float2((float)((double)v.x * c.sa * c.sb), (float)((double)v.y * c.sa * c.sb));
+  strip_track(c, (double)r.x, (double)r.y);
+  return r;
+}
+__device__ __forceinline__ double2 strip_apply(StripCtx& c, double2 v) {
+  const double2 r = make_double2(v.x * c.sa * c.sb, v.y * c.sa * c.sb);
+  strip_track(c, r.x, r.y);
+  return r;
+}
+// all threads of the (converged) warp: one atomicMax per warp; non-negative doubles order like
+// their bit patterns, NaN (sign clear) above everything -- it propagates like the reference's
+__device__ __forceinline__ void strip_end(const StripCtx& c) {
+  if (c.fc == nullptr) return;
+  unsigned long long bits = (unsigned long long)__double_as_longlong(c.run != c.run ? __longlong_as_double(0x7ff8000000000000LL) : c.run);
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) {
+    const unsigned long long o = __shfl_xor_sync(0xffffffffu, bits, d);
+    bits = o > bits ? o : bits;
+  }
+  if ((threadIdx.x & 31) == 0 && bits != 0ull) atomicMax(c.fc, bits);
+}
+
 // ------------------------------------------------------------------ cp.async
 template <int BYTES>
 __device__ __forceinline__ void cp_async_zfill(void* smem_dst, const void* gsrc, bool valid) {
@@ -469,6 +542,7 @@ struct DmmaPolicy {
 #include "rowstream.cuh"
 #include "dmmastream.cuh"
 #include "dotstream.cuh"
+#include "dotdmma.cuh"
 #include "tc05_policy.cuh"
 #include "gett_ws.cuh"
 #include "tc05_kernel.cuh"
@@ -505,7 +579,8 @@ __global__ void single_kernel(const int64_t* __restrict__ D, const T* __restrict
 }
 
 // ------------------------------------------------------------------ strip_exponent helpers
-// contract.py:816-829: factor = max|p|; exponent += log10(factor); p /= factor.
+// contract.py:816-829: factor = max|p|; exponent += log10(factor); p /= factor  (fused into the
+// kernels' epilogues, StripCtx above; absmax_kernel serves the nodes that add partial sums atomically)
 __device__ __forceinline__ double abs_of(float v) { return fabs((double)v); }
 __device__ __forceinline__ double abs_of(double v) { return fabs(v); }
 __device__ __forceinline__ double abs_of(float2 v) { return hypot((double)v.x, (double)v.y); }
@@ -531,28 +606,6 @@ __global__ void absmax_kernel(const T* __restrict__ p, long long n, unsigned lon
   if ((threadIdx.x & 31) == 0) atomicMax(slot, bits);
 }
 
-__device__ __forceinline__ float scale_of(float v, double s) { return (float)(v / (float)s); }
-__device__ __forceinline__ double scale_of(double v, double s) { return v / s; }
-__device__ __forceinline__ float2 scale_of(float2 v, double s) {
-  float f = (float)s;
-  return make_float2(v.x / f, v.y / f);
-}
-__device__ __forceinline__ double2 scale_of(double2 v, double s) { return make_double2(v.x / s, v.y / s); }
-
-// p /= factor ; exponent += log10(factor)   (block 0 / thread 0 updates the exponent)
-template <typename T>
-__global__ void strip_kernel(T* __restrict__ p, long long n, const unsigned long long* __restrict__ slot,
-                             double* __restrict__ exponent) {
-  const double f = __longlong_as_double((long long)*slot);
-  // an all-zero intermediate (contract.py:819-820, check_zero): keep the zeros instead of 0/0
-  // and make the exponent -inf; it stays -inf through every later node of the slice, and the
-  // exponent-aware adder below gives such a slice weight 10^-inf = 0 (core.py:163-170)
-  if (f != 0.0)
-    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
-      p[i] = scale_of(p[i], f);
-  if (blockIdx.x == 0 && threadIdx.x == 0) *exponent += (f != 0.0) ? log10(f) : -CUDART_INF;
-}
-
 __device__ __forceinline__ float mulr_of(float v, double s) { return (float)(v * s); }
 __device__ __forceinline__ double mulr_of(double v, double s) { return v * s; }
 __device__ __forceinline__ float2 mulr_of(float2 v, double s) { return make_float2((float)(v.x * s), (float)(v.y * s)); }
@@ -573,10 +626,13 @@ __global__ void rescale_out_kernel(T* __restrict__ out, long long n, const doubl
 }
 template <typename T>
 __global__ void add_chunk_kernel(const int64_t* __restrict__ D, T* __restrict__ out, const T* __restrict__ m,
-                                 const double* __restrict__ E, const double* __restrict__ es) {
+                                 const double* __restrict__ E, const double* __restrict__ es,
+                                 const double* __restrict__ froot) {
   // D: single-operand descriptor mapping the dense slice result onto the chunk
+  // froot: the root's own factor max|m| -- the stored root is not normalised yet (lazy scaling)
   const double e = fmax(*E, *es);
-  const double sn = (*es == e) ? 1.0 : pow(10.0, *es - e);
+  double sn = (*es == e) ? 1.0 : pow(10.0, *es - e);
+  if (froot != nullptr) sn = (*froot != 0.0) ? sn / *froot : 0.0;
   const int n_o = (int)D[S_NO];
   const long long n = D[S_OUT_ELEMS];
   for (long long o = blockIdx.x * (long long)blockDim.x + threadIdx.x; o < n; o += (long long)gridDim.x * blockDim.x) {
@@ -594,8 +650,29 @@ __global__ void add_chunk_kernel(const int64_t* __restrict__ D, T* __restrict__ 
 __global__ void commit_exponent_kernel(double* __restrict__ E, const double* __restrict__ es) {
   *E = fmax(*E, *es);
 }
+// fused strip_exponent bookkeeping: factor slots of the listed tensors back to zero
+__global__ void reset_slots_kernel(double* __restrict__ f, const int* __restrict__ list, int n) {
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) f[list[i]] = 0.0;
+}
+// exponent = base + sum_i log10(factor[list[i]])   (-inf as soon as one factor is zero; one block)
+__global__ void sum_log_kernel(const double* __restrict__ f, const int* __restrict__ list, int n,
+                               double* __restrict__ exponent, const double* __restrict__ base) {
+  __shared__ double part[8];
+  double acc = 0.0;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    const double v = f[list[i]];
+    acc += (v != 0.0) ? log10(v) : -CUDART_INF;
+  }
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, d);
+  if ((threadIdx.x & 31) == 0) part[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t = base ? *base : 0.0;
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) t += part[w];
+    *exponent = t;
+  }
+}
 __global__ void set_double_kernel(double* p, double v) { *p = v; }
-__global__ void copy_double_kernel(double* dst, const double* src) { *dst = *src; }
-__global__ void zero_slot_kernel(unsigned long long* p) { *p = 0ull; }
 
 }  // namespace ctgb

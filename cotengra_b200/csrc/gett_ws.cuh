@@ -405,6 +405,7 @@ gett_kernel(const int64_t* __restrict__ D, const T* __restrict__ A, const T* __r
     const int ktext = (int)D[W_KTEXT], kfull = (int)D[W_KFULL], kw = (int)D[W_KW];
     typename P::Acc acc;
     P::clear(acc);
+    StripCtx sctx = strip_begin(D);  // fused strip_exponent (off: one uniform branch per tile)
     unsigned g = 0;
     // the small operand's tile is identical for every work item of this launch
     [[maybe_unused]] const bool b_invariant = steps_k == 1 && n_gn == 0 && n_gb == 0;
@@ -445,7 +446,26 @@ gett_kernel(const int64_t* __restrict__ D, const T* __restrict__ A, const T* __r
       // and the warps sat in instruction-fetch stalls (ncu: 42 % of the epilogue samples of a
       // K=16 node were no_inst, the epilogue 30 % of the consumers' time).
       T* const ctile = C + baseC;
-      if (pair_ok && m_valid == MT && n_valid == NT) {
+      if (sctx.scale) {
+        // strip_exponent: scale by 1/(fA fB), record max|C| (split-K partial sums are only
+        // scaled: fc is null and the host measures C afterwards); one generic store path
+        P::epilogue(
+            acc, scratch,
+            [&](int r, int c, T v) {
+              if (r < m_valid && c < n_valid) {
+                v = strip_apply(sctx, v);
+                T* p = ctile + offMC[r] + offNC[c];
+                if (atomic) {
+                  atomic_add_of(p, v);
+                } else if (accumulate) {
+                  *p = add_of(*p, v);
+                } else {
+                  *p = v;
+                }
+              }
+            },
+            [&](int, int, T, T) {}, false, n_valid);
+      } else if (pair_ok && m_valid == MT && n_valid == NT) {
         P::epilogue(
             acc, scratch, [&](int r, int c, T v) { ctile[offMC[r] + offNC[c]] = v; },
             [&](int r, int c, T v0, T v1) { store_pair_of(ctile + offMC[r] + offNC[c], v0, v1); }, true, n_valid);
@@ -487,6 +507,7 @@ gett_kernel(const int64_t* __restrict__ D, const T* __restrict__ A, const T* __r
       }
       P::clear(acc);
     }
+    strip_end(sctx);
   }
 }
 

@@ -11,7 +11,9 @@
 
 constexpr int RS_MAXDIMS = MAX_T + MAX_G;
 
-template <typename T, int NMAX, int KMAX, bool BREG>
+// STRIP: fused strip_exponent (a separate instantiation: its few live registers would spill
+// inside the row loop of the register-bound variants otherwise)
+template <typename T, int NMAX, int KMAX, bool BREG, bool STRIP = false>
 __global__ void __launch_bounds__(256, BREG ? 2 : 3)
 rowstream_kernel(const int64_t* __restrict__ D, const T* __restrict__ A, const T* __restrict__ B, T* __restrict__ C) {
   __shared__ long long s_akoff[KMAX], s_bkoff[KMAX], s_bnoff[NMAX], s_cnoff[NMAX];
@@ -91,6 +93,8 @@ rowstream_kernel(const int64_t* __restrict__ D, const T* __restrict__ A, const T
 #pragma unroll
   for (int kk = 0; kk < KMAX; ++kk) akoff[kk] = s_akoff[kk];
 
+  [[maybe_unused]] StripCtx sctx;
+  if constexpr (STRIP) sctx = strip_begin(D);
   const unsigned long long M = (unsigned long long)D[W_MTA] * (unsigned long long)D[W_TILES_M];
   const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
   // rows per thread and iteration: narrow element types need more loads in flight
@@ -158,6 +162,11 @@ rowstream_kernel(const int64_t* __restrict__ D, const T* __restrict__ A, const T
             }
           }
         }
+        if constexpr (STRIP) {
+#pragma unroll
+          for (int c = 0; c < CH; ++c)
+            if (c0 + c < N) acc[c] = strip_apply(sctx, acc[c]);
+        }
         bool done = false;
         if constexpr (sizeof(T) == 8) {
           if (quad8) {
@@ -197,4 +206,5 @@ rowstream_kernel(const int64_t* __restrict__ D, const T* __restrict__ A, const T
       }
     }
   }
+  if constexpr (STRIP) strip_end(sctx);
 }

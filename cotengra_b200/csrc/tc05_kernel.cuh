@@ -446,6 +446,7 @@ tc05_kernel(const int64_t* __restrict__ D, const float2* __restrict__ A, const f
     const int quad = warp & 3;  // TMEM lane quadrant of this warp
     const int r = quad * 32 + lane;
     const long long row_off = offMC[r];
+    StripCtx sctx = strip_begin(D);  // fused strip_exponent
     for (unsigned j = 0; j < nw; ++j) {
       const unsigned buf = j & 1;
       mbar_wait(&tmem_full[buf], (j >> 1) & 1);
@@ -477,6 +478,14 @@ tc05_kernel(const int64_t* __restrict__ D, const float2* __restrict__ A, const f
         asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
 #pragma unroll
         for (int i = 0; i < 32; ++i) v[i] = __float_as_uint(__uint_as_float(v[i]) + __uint_as_float(u[i]));
+        if (sctx.scale) {
+#pragma unroll
+          for (int i = 0; i < 32; i += 2) {
+            const float2 z = strip_apply(sctx, make_float2(__uint_as_float(v[i]), __uint_as_float(v[i + 1])));
+            v[i] = __float_as_uint(z.x);
+            v[i + 1] = __float_as_uint(z.y);
+          }
+        }
 #pragma unroll
         for (int s4 = 0; s4 < 4; ++s4) {  // groups of 4 complex columns
           const int c0 = (col >> 1) + s4 * 4;
@@ -507,6 +516,7 @@ tc05_kernel(const int64_t* __restrict__ D, const float2* __restrict__ A, const f
       __syncwarp();
       if (lane == 0) mbar_arrive(&tmem_empty[buf]);
     }
+    strip_end(sctx);
   }
   if (warp < 8) {
     named_sync<2, 256>();

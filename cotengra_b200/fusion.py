@@ -68,10 +68,15 @@ def node_time(dtype, B, M, N, K, elems):
         if K >= 1 << 20:
             return _LAUNCH + nbytes / r["dot"]      # dot-stream kernels
         return _LAUNCH + nbytes / 2.5e12 + flops / 2e12
-    if M < 64 and K >= 1 << 12:
-        # a small result over a long contracted range and no dot-stream kernel for it: tensor
-        # tiles mostly empty (or FMA tiles) with split-K atomics -- far from either roofline
-        return _LAUNCH + max(nbytes / 1.5e12, flops / 3e12)
+    if dtype == "complex128" and M <= 32 and N <= 32 and B == 1 and K >= 1 << 20:
+        # DMMA dot kernel: fragments padded to 16 x 16 or 32 x 32
+        pad = 16 if (M <= 16 and N <= 16) else 32
+        return _LAUNCH + max(nbytes / 6.0e12, 8.0 * pad * pad * K / 30e12)
+    if K >= 1 << 12 and (M < 64 or M * N <= 1 << 14):
+        # a small result over a long contracted range and no dot-stream kernel for it: a handful
+        # of (mostly empty) tensor tiles with split-K atomics -- far from either roofline
+        # (measured: M=128 N=16 K=2^23 complex64 at 1.05 TB/s, 15 TFLOP/s)
+        return _LAUNCH + max(nbytes / 1.0e12, flops / 12e12)
     if N <= 8 and K <= 8 and B == 1:
         bw = r["stream"] if N * K <= 16 else 0.8 * r["stream"]
         return _LAUNCH + nbytes / bw

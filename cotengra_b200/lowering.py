@@ -60,6 +60,7 @@ VAR_SIMT_64x64, VAR_KRED, VAR_DMMA_128x64, VAR_DMMA_64x128, VAR_DMMA_256x32 = 0,
 VAR_DMMA_256x16, VAR_ROW_128x8, VAR_ROW_256x4, VAR_ROWSTREAM = 5, 6, 7, 8
 VAR_TC05_128x64, VAR_TC05_128x32, VAR_TC05_128x16 = 9, 10, 11
 VAR_DMMA3M_128x32, VAR_DMMA3M_256x16, VAR_DMMASTREAM, VAR_DOTSTREAM, VAR_DOTSTREAM4 = 12, 13, 14, 15, 16
+VAR_DOTDMMA = 17
 DMMASTREAM_MAX_N = 16  # the kernel takes N <= 32, but at N = 32 the staged 256x32 policy is faster (31.8 vs 26 TFLOP/s)
 TC05_VARIANTS = (VAR_TC05_128x64, VAR_TC05_128x32, VAR_TC05_128x16)
 # (MT, NT, KT) of every kernel variant -- must match ctg_b200.cu's dispatch
@@ -80,7 +81,8 @@ VARIANT_TILES = {
     VAR_DMMA3M_256x16: (256, 16, 8),
     VAR_DMMASTREAM: (256, 32, 32),
     VAR_DOTSTREAM: (1, 1, 2048),
-    VAR_DOTSTREAM4: (4, 4, 512),
+    VAR_DOTSTREAM4: (4, 4, 1024),
+    VAR_DOTDMMA: (32, 32, 128),
 }
 
 DTYPE_CODES = {"float32": 0, "float64": 1, "complex64": 2, "complex128": 3}
@@ -332,6 +334,9 @@ def choose_variant(dtype, B, M, N, K, allow_dmma=True, allow_stream=True, allow_
         return VAR_DOTSTREAM
     if M <= 4 and N <= 4 and B == 1 and K >= 1 << 20 and allow_stream:
         return VAR_DOTSTREAM4  # a stem tail peeled over the final inner product (fusion.py)
+    if (dtype == "complex128" and allow_dmma and allow_stream and M <= 32 and N <= 32 and B == 1
+            and K >= 1 << 20):
+        return VAR_DOTDMMA     # the same with a few more peeled tensors: DMMA fragments from global
     if M == 1 and N == 1 and B == 1 and K >= 8192:
         return VAR_KRED
     if N <= 8 and K <= 8 and B == 1 and 64 <= M < 1 << 32 and allow_stream:
@@ -511,6 +516,14 @@ def build_pair_desc(dims: PairDims, dtype, accumulate=False, sm_count=148,
                                      or pm is not None or pn is not None
                                      or (pk is not None and pk[1] % pk[2] != 0)
                                      or not (accumulate or c_dense_elems == M * N)):
+        return build_pair_desc(dims, dtype, accumulate=accumulate, sm_count=sm_count, variant=VAR_SIMT_64x64,
+                               allow_dmma=allow_dmma, c_dense_elems=c_dense_elems, force_splitk=force_splitk)
+    if variant == VAR_DOTDMMA and (not (dtype == "complex128" and M <= 32 and N <= 32 and B == 1) or len(gk) > 40
+                                  or steps_k >= 1 << 31 or pm is not None or pn is not None or pk is not None
+                                  or KTa != KT or not (accumulate or c_dense_elems == M * N)
+                                  # (32-bit tile-local offsets in the kernel)
+                                  or sum((d[0] - 1) * abs(d[1]) for d in tm + tk) >= 1 << 32
+                                  or sum((d[0] - 1) * abs(d[1]) for d in tn) + sum((d[0] - 1) * abs(d[2]) for d in tk) >= 1 << 32):
         return build_pair_desc(dims, dtype, accumulate=accumulate, sm_count=sm_count, variant=VAR_SIMT_64x64,
                                allow_dmma=allow_dmma, c_dense_elems=c_dense_elems, force_splitk=force_splitk)
     if variant == VAR_DMMASTREAM and (pn is not None or pk is not None or (pm is not None and pm[1] % pm[2] != 0)):

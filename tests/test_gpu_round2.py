@@ -129,6 +129,25 @@ def test_dotstream4_pair(dtype, mn):
     del torch
 
 
+@pytest.mark.parametrize("mn", [(32, 32), (16, 32), (8, 8), (5, 20), (32, 4), (16, 16)])
+def test_dotdmma_pair(mn):
+    """complex128, M, N <= 32 over K = 2^21: DMMA fragments straight from global memory
+    (peeled stem tails, fusion.py)."""
+    M, N = mn
+    shape_a = (8, 64, M, 4, 1024)          # a, b, m, c, d
+    shape_b = (1024, N, 4, 8, 64)          # d, n, c, a, b
+    a, b = make_arrays([shape_a, shape_b], "complex128", seed=9)
+    dims = L.classify_pair("abmcd", shape_a, "dncab", shape_b, "mn")
+    plan = L.build_pair_desc(dims, "complex128", c_dense_elems=M * N)
+    assert plan.variant == (L.VAR_DOTSTREAM4 if max(M, N) <= 4 else L.VAR_DOTDMMA)
+    got = cb.einsum("abmcd,dncab->mn", a, b)
+    want = np.einsum("abmcd,dncab->mn", a, b)
+    assert rel_err(got, want) < 1e-10
+    # and into a permuted (strided) output through the tree executor's root path
+    got2 = cb.einsum("abmcd,dncab->nm", a, b)
+    assert rel_err(got2, want.T) < 1e-10
+
+
 def test_dotstream4_ragged_k_falls_back():
     a, b = make_arrays([(3, 1000003), (1000003, 4)], "complex128", seed=5)
     dims = L.classify_pair("mk", a.shape, "kn", b.shape, "mn")
@@ -244,7 +263,8 @@ def test_operand_beyond_2_31_elements(case):
     elif case == "tc05_c64":
         M, K, N, dt, tol = 2**25, 128, 64, torch.complex64, 2e-5
     else:
-        M, K, N, dt, tol = 2**25, 64, 64, torch.complex128, 1e-10
+        # 2^31 + 2^26 elements per operand, ragged row count (partial last tile)
+        M, K, N, dt, tol = 2**25 + 2**20 + 24, 64, 64, torch.complex128, 1e-10
     a = torch.empty((M, K), dtype=dt, device="cuda")
     torch.view_as_real(a).uniform_(-1, 1, generator=gen)
     b = torch.empty((K, N), dtype=dt, device="cuda")
@@ -257,7 +277,8 @@ def test_operand_beyond_2_31_elements(case):
     assert plan.variant in want_var, plan.variant
     got = cb.einsum("mk,kn->mn", a, b)
     half = (2**31) // K
-    rows = [0, half - 64, half, half + 4096, M - 64]
+    rows = [r0 for r0 in (0, half - 64, half, half + 4096, M - 64) if 0 <= r0 <= M - 64]
+    assert rows[-1] * K + 64 * K > 2**31
     _check_rows(got, a, b, "mk,kn->mn", rows, tol)
     del a, b, got
     torch.cuda.empty_cache()
