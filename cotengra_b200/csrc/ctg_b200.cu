@@ -237,7 +237,10 @@ int launch_dmmastream(const int64_t* h, const int64_t* d, const void* A, const v
   if (blocks > cap) blocks = cap;
   const bool strip = h[W_SCALE_A] != 0;  // fused strip_exponent: separate instantiations
   const double2 *a = (const double2*)A, *b = (const double2*)B;
-  if (N <= 16) {
+  if (N <= 8) {
+    if (strip) dmmastream_kernel<1, true><<<(unsigned)blocks, 128, 0, st>>>(d, a, b, (double2*)C);
+    else dmmastream_kernel<1><<<(unsigned)blocks, 128, 0, st>>>(d, a, b, (double2*)C);
+  } else if (N <= 16) {
     if (strip) dmmastream_kernel<2, true><<<(unsigned)blocks, 128, 0, st>>>(d, a, b, (double2*)C);
     else dmmastream_kernel<2><<<(unsigned)blocks, 128, 0, st>>>(d, a, b, (double2*)C);
   } else {
@@ -346,6 +349,7 @@ int launch_gett_typed(const int64_t* h, const int64_t* d, const void* A, const v
       case VAR_DMMA_64x128: return launch_gett_policy<T, DmmaPolicy<T, 2, 4, 4, 4, 16, 3>>(h, d, A, B, C, st);
       case VAR_DMMA_256x32: return launch_gett_policy<T, DmmaPolicy<T, 8, 1, 4, 4, 8, 4>>(h, d, A, B, C, st);
       case VAR_DMMA_256x16: return launch_gett_policy<T, DmmaPolicy<T, 8, 1, 4, 2, 8, 5>>(h, d, A, B, C, st);
+      case VAR_DMMA_32x32: return launch_gett_policy<T, DmmaPolicy<T, 2, 2, 2, 2, 32, 3>>(h, d, A, B, C, st);
       default: break;
     }
   }

@@ -1,5 +1,5 @@
 // dmmastream.cuh -- fp64 tensor-core streaming kernel for narrow complex128 nodes
-// (8 < N <= 8*NJ, K <= 32, no batch): the rowstream idea with DMMA fragments.
+// (N <= 8*NJ, K <= 64, no batch): the rowstream idea with DMMA fragments.
 //
 // Every warp owns blocks of 32 output rows and runs them start to finish on its own:
 // A fragments straight from global memory into registers (a lane of the m8k4 A fragment
@@ -12,10 +12,12 @@
 // (included inside namespace ctgb)
 #pragma once
 
-constexpr int DS_KMAX = 32;
+constexpr int DS_KMAX = 64;
 
-// NJ = column fragments (N <= 8*NJ).  128 threads x 3 blocks (NJ = 2: <= 170 registers) or x 2 blocks
-// (NJ = 4: 128 accumulator registers), 16 loads in flight per lane
+// NJ = column fragments (N <= 8*NJ).  128 threads x 3 blocks (NJ <= 2: <= 170 registers) or x 2 blocks
+// (NJ = 4: 128 accumulator registers), 16 loads in flight per lane.  NJ = 1 serves skinny nodes
+// whose contracted space is too long for the row-stream kernel (N <= 8, 8 < K <= 64: the staged
+// row policy ran the M = 2^22, N = 8, K = 64 node of the Sycamore slice at 0.57 of its roofline)
 template <int NJ, bool STRIP = false>
 __global__ void __launch_bounds__(128, NJ <= 2 ? 3 : 2)
 dmmastream_kernel(const int64_t* __restrict__ D, const double2* __restrict__ A, const double2* __restrict__ B,

@@ -82,7 +82,8 @@ enum : int {
   VAR_DOTSTREAM = 15,      // M = N = 1: the final inner product, operands straight from global memory
   VAR_DMMASTREAM = 14,     // complex128, 8 < N <= 16, K <= 32: DMMA fragments straight from global memory
   VAR_DOTSTREAM4 = 16,     // M, N <= 4 over a huge contracted range: a peeled stem tail times the other stem
-  VAR_DOTDMMA = 17         // complex128, M, N <= 32 over a huge contracted range: the same on DMMA fragments
+  VAR_DOTDMMA = 17,        // complex128, M, N <= 32 over a huge contracted range: the same on DMMA fragments
+  VAR_DMMA_32x32 = 18      // fp64 DMMA, one 32 x 32 tile with split-K over all SMs (staged): the same node shape
 };
 
 // ---- single-operand descriptor (cotengra/contract.py:332-361) -------------

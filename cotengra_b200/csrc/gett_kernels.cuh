@@ -90,10 +90,13 @@ __device__ __forceinline__ double2 shfl_down_of(double2 v, int d) {
 // forms, (A/fA)(B/fB), since the product is bilinear -- and the exponent is the sum of
 // log10(factor) over the nodes, formed once per slice.
 struct StripCtx {
-  double sa, sb;            // 1/fA, 1/fB (0 when the operand is identically zero: check_zero)
+  double s;                 // 1/(fA fB): one multiply per component (0 when an operand is identically
+                            // zero: check_zero)
+  double sb;                // second factor, only used when the product 1/fA * 1/fB leaves the double range
+  float sf;                 // s as a float when it is a normal float (single precision kernels), else 0
   double run;               // largest |value| this thread has stored
   unsigned long long* fc;   // factor slot of C (nullptr: the caller measures C separately)
-  bool scale;
+  bool scale, two;
 };
 __device__ __forceinline__ StripCtx strip_begin(const int64_t* __restrict__ D) {
   StripCtx c;
@@ -102,11 +105,20 @@ __device__ __forceinline__ StripCtx strip_begin(const int64_t* __restrict__ D) {
   c.scale = pa != nullptr;
   c.fc = reinterpret_cast<unsigned long long*>(D[W_FACTOR_C]);
   c.run = 0.0;
-  c.sa = c.sb = 1.0;
+  c.s = c.sb = 1.0;
+  c.sf = 1.f;
+  c.two = false;
   if (c.scale) {
     const double fa = *pa, fb = *pb;
-    c.sa = fa != 0.0 ? 1.0 / fa : 0.0;
-    c.sb = fb != 0.0 ? 1.0 / fb : 0.0;
+    const double sa = fa != 0.0 ? 1.0 / fa : 0.0, sb = fb != 0.0 ? 1.0 / fb : 0.0;
+    const double prod = sa * sb;
+    // (1/fA)(1/fB) overflows or underflows only for factors near the ends of the double range
+    c.two = (sa != 0.0 && sb != 0.0) && (prod == 0.0 || prod > 1.7e308);
+    c.s = c.two ? sa : prod;
+    c.sb = c.two ? sb : 1.0;
+    const double ap = fabs(prod);
+    c.sf = (!c.two && (ap == 0.0 || (ap > 1e-30 && ap < 1e30))) ? (float)prod : 0.f;
+    // (sf == 0 with s != 0: single precision kernels fall back to the double multiply)
   }
   return c;
 }
@@ -121,23 +133,33 @@ __device__ __forceinline__ void strip_track(StripCtx& c, double re, double im) {
     c.run = (h != h) ? h : fmax(c.run, h);
   }
 }
+__device__ __forceinline__ void strip_track_f(StripCtx& c, float re, float im) {
+  // single precision: the cheap test in float (exact: a sum of two non-negative floats rounded
+  // up or down still bounds nothing wrongly -- the test is only a filter, hypot decides)
+  const float a = fabsf(re) + fabsf(im);
+  if (!((double)a * 0.999999 <= c.run)) strip_track(c, (double)re, (double)im);
+}
+__device__ __forceinline__ double strip_mul(const StripCtx& c, double v) { return c.two ? v * c.s * c.sb : v * c.s; }
+__device__ __forceinline__ float strip_mul(const StripCtx& c, float v) {
+  return (c.sf != 0.f || c.s == 0.0) ? v * c.sf : (float)strip_mul(c, (double)v);
+}
 __device__ __forceinline__ float strip_apply(StripCtx& c, float v) {
-  const float r = (float)((double)v * c.sa * c.sb);
-  strip_track(c, (double)r, 0.0);
+  const float r = strip_mul(c, v);
+  strip_track_f(c, r, 0.f);
   return r;
 }
 __device__ __forceinline__ double strip_apply(StripCtx& c, double v) {
-  const double r = v * c.sa * c.sb;
+  const double r = strip_mul(c, v);
   strip_track(c, r, 0.0);
   return r;
 }
 __device__ __forceinline__ float2 strip_apply(StripCtx& c, float2 v) {
-  const float2 r = make_float2((float)((double)v.x * c.sa * c.sb), (float)((double)v.y * c.sa * c.sb));
-  strip_track(c, (double)r.x, (double)r.y);
+  const float2 r = make_float2(strip_mul(c, v.x), strip_mul(c, v.y));
+  strip_track_f(c, r.x, r.y);
   return r;
 }
 __device__ __forceinline__ double2 strip_apply(StripCtx& c, double2 v) {
-  const double2 r = make_double2(v.x * c.sa * c.sb, v.y * c.sa * c.sb);
+  const double2 r = make_double2(strip_mul(c, v.x), strip_mul(c, v.y));
   strip_track(c, r.x, r.y);
   return r;
 }
@@ -415,7 +437,7 @@ struct DmmaPolicy {
   // 8 consumer warps x 232 + 4 producer warps x 40 registers = 64512 <= 65536
   static constexpr int CONSUMER_REGS = (THREADS == 256) ? 232 : 0, PRODUCER_REGS = 40;
   static constexpr bool HAS_BCACHE = false;
-  static constexpr int MIN_BLOCKS = 1;
+  static constexpr int MIN_BLOCKS = THREADS <= 128 ? 2 : 1;  // the 32 x 32 split-K policy: two CTAs per SM
   static_assert(KT % 4 == 0, "KT must be a multiple of the DMMA k");
   struct Acc {
     double re[FM][FN][2];

@@ -446,9 +446,18 @@ gett_kernel(const int64_t* __restrict__ D, const T* __restrict__ A, const T* __r
       // and the warps sat in instruction-fetch stalls (ncu: 42 % of the epilogue samples of a
       // K=16 node were no_inst, the epilogue 30 % of the consumers' time).
       T* const ctile = C + baseC;
-      if (sctx.scale) {
-        // strip_exponent: scale by 1/(fA fB), record max|C| (split-K partial sums are only
-        // scaled: fc is null and the host measures C afterwards); one generic store path
+      if (sctx.scale && pair_ok && m_valid == MT && n_valid == NT) {
+        // strip_exponent, full tile with 256-bit stores: scale by 1/(fA fB), record max|C|
+        P::epilogue(
+            acc, scratch, [&](int r, int c, T v) { ctile[offMC[r] + offNC[c]] = strip_apply(sctx, v); },
+            [&](int r, int c, T v0, T v1) {
+              const T w0 = strip_apply(sctx, v0), w1 = strip_apply(sctx, v1);
+              store_pair_of(ctile + offMC[r] + offNC[c], w0, w1);
+            },
+            true, n_valid);
+      } else if (sctx.scale) {
+        // ... every other store mode (split-K partial sums are only scaled: fc is null and the
+        // host measures C afterwards)
         P::epilogue(
             acc, scratch,
             [&](int r, int c, T v) {

@@ -80,17 +80,22 @@ def node_time(dtype, B, M, N, K, elems):
     if N <= 8 and K <= 8 and B == 1:
         bw = r["stream"] if N * K <= 16 else 0.8 * r["stream"]
         return _LAUNCH + nbytes / bw
+    if dtype == "complex128" and B == 1 and ((N <= 16 and K <= 32) or (N <= 8 and K <= 64)):
+        return _LAUNCH + max(nbytes / r["dstream"], flops * (8.0 / N if N < 8 else 1.0) / r["dstream_tf"])
     if N <= 8:
         return _LAUNCH + max(nbytes / 3.7e12, flops / 13e12)  # staged row policy
     if dtype == "complex128" and N <= 16 and K <= 32 and B == 1:
         return _LAUNCH + max(nbytes / r["dstream"], flops / r["dstream_tf"])
     tf = r["tf"][64 if K >= 64 else 32 if K >= 32 else 16 if K >= 16 else 0]
+    staged_bw = r["staged"]
     if N < 24:
         tf *= 0.8
+        if dtype == "complex64":
+            staged_bw = 3.2e12  # tcgen05 128 x 16 tiles: measured on the M = 2^26, N = K = 16 node
     # tile occupancy of the staged tensor-core variants (lowering.choose_variant)
     MT, NT = (64, 128) if N >= 96 else (128, 64) if N >= 48 else (256, 32) if N >= 24 else (256, 16)
     util = (M / (-(-M // MT) * MT)) * (N / (-(-N // NT) * NT))
-    return _LAUNCH + max(nbytes / r["staged"], flops / (tf * util))
+    return _LAUNCH + max(nbytes / staged_bw, flops / (tf * util))
 
 
 class _Node:

@@ -24,6 +24,7 @@ own planners (tests/test_lowering.py).
 from __future__ import annotations
 
 import math
+import os
 from dataclasses import dataclass, field
 
 import numpy as np
@@ -60,7 +61,7 @@ VAR_SIMT_64x64, VAR_KRED, VAR_DMMA_128x64, VAR_DMMA_64x128, VAR_DMMA_256x32 = 0,
 VAR_DMMA_256x16, VAR_ROW_128x8, VAR_ROW_256x4, VAR_ROWSTREAM = 5, 6, 7, 8
 VAR_TC05_128x64, VAR_TC05_128x32, VAR_TC05_128x16 = 9, 10, 11
 VAR_DMMA3M_128x32, VAR_DMMA3M_256x16, VAR_DMMASTREAM, VAR_DOTSTREAM, VAR_DOTSTREAM4 = 12, 13, 14, 15, 16
-VAR_DOTDMMA = 17
+VAR_DOTDMMA, VAR_DMMA_32x32 = 17, 18
 DMMASTREAM_MAX_N = 16  # the kernel takes N <= 32, but at N = 32 the staged 256x32 policy is faster (31.8 vs 26 TFLOP/s)
 TC05_VARIANTS = (VAR_TC05_128x64, VAR_TC05_128x32, VAR_TC05_128x16)
 # (MT, NT, KT) of every kernel variant -- must match ctg_b200.cu's dispatch
@@ -79,10 +80,11 @@ VARIANT_TILES = {
     VAR_TC05_128x16: (128, 16, 16),
     VAR_DMMA3M_128x32: (128, 32, 16),
     VAR_DMMA3M_256x16: (256, 16, 8),
-    VAR_DMMASTREAM: (256, 32, 32),
+    VAR_DMMASTREAM: (256, 32, 64),
     VAR_DOTSTREAM: (1, 1, 2048),
     VAR_DOTSTREAM4: (4, 4, 1024),
     VAR_DOTDMMA: (32, 32, 128),
+    VAR_DMMA_32x32: (32, 32, 32),
 }
 
 DTYPE_CODES = {"float32": 0, "float64": 1, "complex64": 2, "complex128": 3}
@@ -336,17 +338,20 @@ def choose_variant(dtype, B, M, N, K, allow_dmma=True, allow_stream=True, allow_
         return VAR_DOTSTREAM4  # a stem tail peeled over the final inner product (fusion.py)
     if (dtype == "complex128" and allow_dmma and allow_stream and M <= 32 and N <= 32 and B == 1
             and K >= 1 << 20):
-        return VAR_DOTDMMA     # the same with a few more peeled tensors: DMMA fragments from global
+        # the same with a few more peeled tensors: DMMA fragments from global (DOTDMMA) or one staged
+        # 32 x 32 tile with split-K over all SMs (CTGB_DOT_VARIANT is a measurement knob)
+        return int(os.environ.get("CTGB_DOT_VARIANT", VAR_DOTDMMA))
     if M == 1 and N == 1 and B == 1 and K >= 8192:
         return VAR_KRED
     if N <= 8 and K <= 8 and B == 1 and 64 <= M < 1 << 32 and allow_stream:
         return VAR_ROWSTREAM
+    # narrow complex128 nodes: DMMA fragments streamed from global memory, no staging
+    # (N <= 8 with a contracted space too long for the row-stream kernel included)
+    if (allow_dmma and allow_stream and dtype == "complex128" and B == 1 and 4096 <= M < 1 << 32
+            and ((N <= DMMASTREAM_MAX_N and K <= 32) or (N <= 8 and 8 < K <= 64))):
+        return VAR_DMMASTREAM
     if N <= 8 and M >= 64:
         return VAR_ROW_256x4 if N <= 4 else VAR_ROW_128x8
-    # narrow complex128 nodes: DMMA fragments streamed from global memory, no staging
-    if (allow_dmma and allow_stream and dtype == "complex128" and N <= DMMASTREAM_MAX_N and K <= 32 and B == 1
-            and 4096 <= M < 1 << 32):
-        return VAR_DMMASTREAM
     # complex64 dense nodes with exact power-of-two tiles: tcgen05 (kind::tf32 x3, TMEM)
     if (allow_dmma and allow_tc05 and dtype == "complex64" and M % 128 == 0 and K % 16 == 0
             and K <= 256 and M * N * K >= 1 << 20):
@@ -398,7 +403,7 @@ def build_pair_desc(dims: PairDims, dtype, accumulate=False, sm_count=148,
     if variant in (VAR_DMMA3M_128x32, VAR_DMMA3M_256x16) and dtype != "complex128":
         # the 3M identity is a complex128 kernel: other dtypes take the plain tensor-core tiles
         variant = VAR_DMMA_256x32 if variant == VAR_DMMA3M_128x32 else VAR_DMMA_256x16
-    if variant == VAR_DMMASTREAM and not (dtype == "complex128" and N <= 32 and K <= 32 and B == 1 and M < 1 << 32):
+    if variant == VAR_DMMASTREAM and not (dtype == "complex128" and N <= 32 and K <= 64 and B == 1 and M < 1 << 32):
         variant = VAR_DMMA_256x16
     if variant == VAR_ROWSTREAM:
         # (a ragged blocked m dim is caught after tiling, below)
@@ -460,6 +465,8 @@ def build_pair_desc(dims: PairDims, dtype, accumulate=False, sm_count=148,
             splitk = min(steps_k, -(-2 * sm_count // tiles))
         if variant == VAR_KRED:
             splitk = min(steps_k, 4 * sm_count)
+        if variant == VAR_DMMA_32x32 and tiles == 1:
+            splitk = min(steps_k, 2 * sm_count)  # two resident CTAs per SM
     if splitk > 1:
         per = -(-steps_k // splitk)
         splitk = -(-steps_k // per)
@@ -519,8 +526,8 @@ def build_pair_desc(dims: PairDims, dtype, accumulate=False, sm_count=148,
         return build_pair_desc(dims, dtype, accumulate=accumulate, sm_count=sm_count, variant=VAR_SIMT_64x64,
                                allow_dmma=allow_dmma, c_dense_elems=c_dense_elems, force_splitk=force_splitk)
     if variant == VAR_DOTDMMA and (not (dtype == "complex128" and M <= 32 and N <= 32 and B == 1) or len(gk) > 40
-                                  or steps_k >= 1 << 31 or pm is not None or pn is not None or pk is not None
-                                  or KTa != KT or not (accumulate or c_dense_elems == M * N)
+                                  or steps_k >= 1 << 31 or pm is not None or pn is not None
+                                  or (pk is not None and pk[1] % pk[2] != 0) or KTa != KT or not (accumulate or c_dense_elems == M * N)
                                   # (32-bit tile-local offsets in the kernel)
                                   or sum((d[0] - 1) * abs(d[1]) for d in tm + tk) >= 1 << 32
                                   or sum((d[0] - 1) * abs(d[1]) for d in tn) + sum((d[0] - 1) * abs(d[2]) for d in tk) >= 1 << 32):

@@ -148,6 +148,20 @@ def test_dotdmma_pair(mn):
     assert rel_err(got2, want.T) < 1e-10
 
 
+@pytest.mark.parametrize("shape", [(1 << 16, 8, 64), (1 << 15, 5, 48), (1 << 14, 8, 16), (12288, 3, 33), (1 << 16, 16, 64)])
+def test_dmmastream_long_k_skinny(shape):
+    """complex128 skinny nodes with a contracted space beyond the row-stream kernel (N <= 8,
+    8 < K <= 64): DMMA fragments from global memory with one column fragment."""
+    M, N, K = shape
+    a, b = make_arrays([(M, K), (K, N)], "complex128", seed=M % 97)
+    dims = L.classify_pair("mk", a.shape, "kn", b.shape, "mn")
+    plan = L.build_pair_desc(dims, "complex128", c_dense_elems=M * N)
+    if N <= 8:
+        assert plan.variant == L.VAR_DMMASTREAM, plan.variant
+    got = cb.einsum("mk,kn->mn", a, b)
+    assert rel_err(got, a @ b) < 1e-10
+
+
 def test_dotstream4_ragged_k_falls_back():
     a, b = make_arrays([(3, 1000003), (1000003, 4)], "complex128", seed=5)
     dims = L.classify_pair("mk", a.shape, "kn", b.shape, "mn")
