@@ -151,7 +151,7 @@ int launch_rowstream(const int64_t* h, const int64_t* d, const void* A, const vo
   const T* a = (const T*)A;
   const T* b = (const T*)B;
   T* c = (T*)C;
-  const bool strip = h[W_SCALE_A] != 0;  // fused strip_exponent: separate instantiations
+  const bool strip = h[W_SCALE_A] != 0 || h[W_FACTOR_C] != 0;  // fused strip_exponent: separate instantiations
   if (N <= 4 && K <= 4) {
     if (strip) rowstream_kernel<T, 4, 4, true, true><<<(unsigned)blocks, 256, 0, st>>>(d, a, b, c);
     else rowstream_kernel<T, 4, 4, true><<<(unsigned)blocks, 256, 0, st>>>(d, a, b, c);
@@ -172,7 +172,7 @@ int launch_dotstream(const int64_t* h, const int64_t* d, const void* A, const vo
   DevInfo& di = devinfo();
   if (!di.ok) return fail(CTGB_E_CUDA, "no CUDA device");
   const bool mn = h[W_VARIANT] == VAR_DOTSTREAM4;
-  const int lim = mn ? DOT4_MN : 1, kt = mn ? DOT4_KT : DOT_KT;
+  const int lim = mn ? DOT4_MN : 1, kt = mn ? dot4_kt<T>() : DOT_KT;
   if (h[W_MTA] > lim || h[W_NTA] > lim || h[W_TILES_M] != 1 || h[W_TILES_N] != 1 || h[W_TILES_B] != 1 ||
       h[W_KTA] > kt || h[W_NGK] > 64 || h[W_STEPS_K] >= (1ll << 31) || h[W_PGM] >= 0 || h[W_PGN] >= 0 ||
       (h[W_PGK] >= 0 && (h[W_KFULL] % h[W_KTEXT]) != 0))
@@ -189,33 +189,9 @@ int launch_dotstream(const int64_t* h, const int64_t* d, const void* A, const vo
   const unsigned long long cap = (unsigned long long)di.sms * (mn ? 1 : 2);
   if (blocks > cap) blocks = cap;
   if (mn)
-    dotstream_kernel<T, DOT4_MN, DOT4_MN, DOT4_U><<<(unsigned)blocks, DOT_THREADS, 0, st>>>(d, (const T*)A, (const T*)B, (T*)C);
+    dotstream_kernel<T, DOT4_MN, DOT4_MN, dot4_u<T>()><<<(unsigned)blocks, DOT_THREADS, 0, st>>>(d, (const T*)A, (const T*)B, (T*)C);
   else
     dotstream_kernel<T, 1, 1, DOT_U><<<(unsigned)blocks, DOT_THREADS, 0, st>>>(d, (const T*)A, (const T*)B, (T*)C);
-  g_launches.fetch_add(1, std::memory_order_relaxed);
-  CUDA_TRY(cudaGetLastError());
-  return CTGB_OK;
-}
-
-int launch_dotdmma(const int64_t* h, const int64_t* d, const void* A, const void* B, void* C, cudaStream_t st) {
-  DevInfo& di = devinfo();
-  if (!di.ok) return fail(CTGB_E_CUDA, "no CUDA device");
-  if (h[W_DTYPE] != CTGB_C128 || h[W_MTA] > 32 || h[W_NTA] > 32 || h[W_TILES_M] != 1 || h[W_TILES_N] != 1 ||
-      h[W_TILES_B] != 1 || h[W_KTA] != DD_KT || h[W_NGK] > 64 || h[W_STEPS_K] >= (1ll << 31) || h[W_PGM] >= 0 ||
-      h[W_PGN] >= 0 || (h[W_PGK] >= 0 && (h[W_KFULL] % h[W_KTEXT]) != 0))
-    return fail(CTGB_E_VALUE, "descriptor does not fit the DMMA dot kernel");
-  if (h[W_STEPS_K] == 0) return CTGB_OK;
-  if (!(h[W_FLAGS] & 1)) {
-    const long long celems = h[W_MTA] * h[W_NTA];
-    if (h[W_CELEMS] != celems) return fail(CTGB_E_VALUE, "DMMA dot into a strided C needs accumulate");
-    CUDA_TRY(cudaMemsetAsync(C, 0, (size_t)celems * sizeof(double2), st));
-  }
-  unsigned long long blocks = (unsigned long long)h[W_STEPS_K];
-  if (blocks > (unsigned long long)di.sms) blocks = (unsigned long long)di.sms;  // one block per SM, one wave
-  if (h[W_MTA] <= 16 && h[W_NTA] <= 16)
-    dotdmma_kernel<2, 2><<<(unsigned)blocks, DD_WARPS * 32, 0, st>>>(d, (const double2*)A, (const double2*)B, (double2*)C);
-  else
-    dotdmma_kernel<4, 4><<<(unsigned)blocks, DD_WARPS * 32, 0, st>>>(d, (const double2*)A, (const double2*)B, (double2*)C);
   g_launches.fetch_add(1, std::memory_order_relaxed);
   CUDA_TRY(cudaGetLastError());
   return CTGB_OK;
@@ -235,7 +211,7 @@ int launch_dmmastream(const int64_t* h, const int64_t* d, const void* A, const v
   unsigned long long blocks = (M + 127) / 128;  // 4 warps x 32 rows per block and pass
   const unsigned long long cap = (unsigned long long)di.sms * 12;
   if (blocks > cap) blocks = cap;
-  const bool strip = h[W_SCALE_A] != 0;  // fused strip_exponent: separate instantiations
+  const bool strip = h[W_SCALE_A] != 0 || h[W_FACTOR_C] != 0;  // fused strip_exponent: separate instantiations
   const double2 *a = (const double2*)A, *b = (const double2*)B;
   if (N <= 8) {
     if (strip) dmmastream_kernel<1, true><<<(unsigned)blocks, 128, 0, st>>>(d, a, b, (double2*)C);
@@ -330,7 +306,6 @@ int launch_gett_typed(const int64_t* h, const int64_t* d, const void* A, const v
   if (variant == VAR_ROWSTREAM) return launch_rowstream<T>(h, d, A, B, C, st);
   if (variant == VAR_DMMASTREAM) return launch_dmmastream(h, d, A, B, C, st);
   if (variant == VAR_DOTSTREAM || variant == VAR_DOTSTREAM4) return launch_dotstream<T>(h, d, A, B, C, st);
-  if (variant == VAR_DOTDMMA) return launch_dotdmma(h, d, A, B, C, st);
   if constexpr (std::is_same<T, float2>::value) {
     if (variant == VAR_TC05_128x64) return launch_tc05<64>(h, d, A, B, C, st);
     if (variant == VAR_TC05_128x32) return launch_tc05<32>(h, d, A, B, C, st);
@@ -413,6 +388,23 @@ unsigned flat_grid(long long n) {
   return (unsigned)b;
 }
 
+template <typename T>
+int scale_copy_typed(const void* src, void* dst, long long n, const double* fa, const double* fb, cudaStream_t st) {
+  scale_copy_kernel<T><<<flat_grid(n), 256, 0, st>>>((const T*)src, (T*)dst, n, fa, fb);
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  CUDA_TRY(cudaGetLastError());
+  return CTGB_OK;
+}
+int scale_copy(int dtype, const void* src, void* dst, long long n, const double* fa, const double* fb, cudaStream_t st) {
+  switch (dtype) {
+    case CTGB_F32: return scale_copy_typed<float>(src, dst, n, fa, fb, st);
+    case CTGB_F64: return scale_copy_typed<double>(src, dst, n, fa, fb, st);
+    case CTGB_C64: return scale_copy_typed<float2>(src, dst, n, fa, fb, st);
+    case CTGB_C128: return scale_copy_typed<double2>(src, dst, n, fa, fb, st);
+  }
+  return fail(CTGB_E_VALUE, "bad dtype");
+}
+
 // max|C| of a node whose own epilogue cannot measure it (split-K / block partial sums)
 template <typename T>
 int absmax_typed(const void* p, long long n, unsigned long long* slot, cudaStream_t st) {
@@ -470,6 +462,7 @@ struct ctgb_plan {
     size_t desc_off;  // word offset into descs
     int64_t c_elems;  // dense elements of the result (strip_exponent)
     int measure_after = 0;  // strip_exponent: max|C| needs its own pass (split-K / block partial sums)
+    int prescale_b = 0;     // strip_exponent: the small operand is copied, scaled by 1/(fA fB), first
   };
   std::vector<Tensor> tensors;
   std::vector<Node> nodes;
@@ -484,6 +477,8 @@ struct ctgb_plan {
   // fused strip_exponent: one factor slot per tensor (1.0 for inputs and single-operand results,
   // max|C| for pairwise results) and the slots to reset / sum per pass
   double* d_factors = nullptr;
+  char* d_bscale = nullptr;     // scaled copy of the current node's small operand
+  size_t bscale_bytes = 0;
   int* d_slot_lists = nullptr;  // [variant slots..., invariant slots...]
   int n_var_slots = 0, n_inv_slots = 0;
   // chunk descriptor for stripped accumulation (host + device), built at create
@@ -628,10 +623,9 @@ int ctgb_plan_create(const ctgb_plan_desc* pd, ctgb_plan** out) {
     q.c_elems = p->tensors[n.c].nbytes / (int64_t)elem_size(pd->dtype);
     if (pd->strip_exponent && n.kind == 0) {
       const int64_t* w = n.desc;
-      q.measure_after = w[W_SPLITK] > 1 || w[W_VARIANT] == VAR_DOTSTREAM || w[W_VARIANT] == VAR_DOTSTREAM4 ||
-                        w[W_VARIANT] == VAR_DOTDMMA;
+      q.measure_after = w[W_SPLITK] > 1 || w[W_VARIANT] == VAR_DOTSTREAM || w[W_VARIANT] == VAR_DOTSTREAM4;
     }
-    if (!n.invariant) per_slice += 1 + q.measure_after;
+    if (!n.invariant) per_slice += 1 + q.measure_after + (pd->strip_exponent && n.kind == 0 ? 1 : 0);
   }
   if (pd->strip_exponent) per_slice += 5;  // reset slots, sum of logs, rescale/add/commit
   p->launches_per_slice = per_slice;
@@ -662,14 +656,23 @@ int ctgb_plan_create(const ctgb_plan_desc* pd, ctgb_plan** out) {
     for (auto& n : p->nodes) {
       if (n.kind != 0) continue;
       int64_t* w = p->descs.data() + n.desc_off;
-      w[W_SCALE_A] = (int64_t)(uintptr_t)(p->d_factors + n.a);
-      w[W_SCALE_B] = (int64_t)(uintptr_t)(p->d_factors + n.b);
+      // small second operand (the usual case on a stem): scale a copy of it instead of every
+      // output element; otherwise the epilogue multiplies by 1/(fA fB)
+      const int64_t bbytes = p->tensors[n.b].nbytes;
+      n.prescale_b = bbytes > 0 && bbytes <= (16ll << 20) && p->tensors[n.b].kind != 3;
+      if (n.prescale_b) {
+        if ((size_t)bbytes > p->bscale_bytes) p->bscale_bytes = (size_t)bbytes;
+      } else {
+        w[W_SCALE_A] = (int64_t)(uintptr_t)(p->d_factors + n.a);
+        w[W_SCALE_B] = (int64_t)(uintptr_t)(p->d_factors + n.b);
+      }
       w[W_FACTOR_C] = n.measure_after ? 0 : (int64_t)(uintptr_t)(p->d_factors + n.c);
       (n.invariant ? inv_slots : var_slots).push_back(n.c);
     }
     p->n_var_slots = (int)var_slots.size();
     p->n_inv_slots = (int)inv_slots.size();
     var_slots.insert(var_slots.end(), inv_slots.begin(), inv_slots.end());
+    if (e == cudaSuccess && p->bscale_bytes) e = cudaMalloc((void**)&p->d_bscale, p->bscale_bytes + 256);
     if (e == cudaSuccess) e = cudaMalloc((void**)&p->d_slot_lists, (var_slots.size() + 1) * sizeof(int));
     if (e == cudaSuccess && !var_slots.empty())
       e = cudaMemcpy(p->d_slot_lists, var_slots.data(), var_slots.size() * sizeof(int), cudaMemcpyHostToDevice);
@@ -721,6 +724,7 @@ void ctgb_plan_destroy(ctgb_plan* p) {
   if (p->d_descs) cudaFree(p->d_descs);
   if (p->d_scalars) cudaFree(p->d_scalars);
   if (p->d_factors) cudaFree(p->d_factors);
+  if (p->d_bscale) cudaFree(p->d_bscale);
   if (p->d_slot_lists) cudaFree(p->d_slot_lists);
   if (p->d_chunk_desc) cudaFree(p->d_chunk_desc);
   if (p->h_stage) cudaFreeHost(p->h_stage);
@@ -786,6 +790,16 @@ int ctgb_plan_execute(ctgb_plan* p, const void* const* inputs, void* out, double
       int rc;
       if (n.kind == 0) {
         char* B = resolve(n.b, out_off);
+        if (n.prescale_b) {
+          // the whole underlying buffer of the small operand (a sliced input keeps its base
+          // offset into the copy), scaled by 1/(fA fB) read from the factor slots on the device
+          const ctgb_plan::Tensor& tb = p->tensors[n.b];
+          char* under = tb.kind == 0 ? (char*)inputs[tb.input_index] : (tb.kind == 1 ? scratch : persistent) + tb.offset;
+          rc = scale_copy(p->dtype, under, p->d_bscale, tb.nbytes / (int64_t)es, p->d_factors + n.a,
+                          p->d_factors + n.b, st);
+          if (rc) return rc;
+          B = p->d_bscale + (B - under);
+        }
         rc = launch_gett(h, d, A, B, C, st);
       } else {
         rc = launch_single(h, d, A, C, st);

@@ -19,7 +19,10 @@ constexpr int DOT_KT = 2048, DOT_THREADS = 256, DOT_U = DOT_KT / DOT_THREADS;
 //   R[m, n] = sum_k A[k, m] * B[k, n],
 // 16 accumulators per thread, 4 k per thread and tile (16 + 16 loads in flight: 128 KB per SM,
 // what the 1x1 kernel needs for 6.9 TB/s; with 2 k it stopped at 5.6 TB/s)
-constexpr int DOT4_MN = 4, DOT4_U = 4, DOT4_KT = DOT4_U * DOT_THREADS;
+constexpr int DOT4_MN = 4;
+// k per thread and tile: 4 for 16-byte elements, 8 for narrower ones (the same 128 KB in flight)
+template <typename T> constexpr int dot4_u() { return sizeof(T) >= 16 ? 4 : 8; }
+template <typename T> constexpr int dot4_kt() { return dot4_u<T>() * DOT_THREADS; }
 
 template <typename T, int MT, int NT, int U>
 __global__ void __launch_bounds__(DOT_THREADS, (MT * NT > 1) ? 1 : 2)

@@ -82,8 +82,10 @@ enum : int {
   VAR_DOTSTREAM = 15,      // M = N = 1: the final inner product, operands straight from global memory
   VAR_DMMASTREAM = 14,     // complex128, 8 < N <= 16, K <= 32: DMMA fragments straight from global memory
   VAR_DOTSTREAM4 = 16,     // M, N <= 4 over a huge contracted range: a peeled stem tail times the other stem
-  VAR_DOTDMMA = 17,        // complex128, M, N <= 32 over a huge contracted range: the same on DMMA fragments
-  VAR_DMMA_32x32 = 18      // fp64 DMMA, one 32 x 32 tile with split-K over all SMs (staged): the same node shape
+  // (17: a DMMA-fragments-from-global variant of the next one, measured slower -- 11.1 vs 10.1 ms on
+  //  the M = N = 32, K = 2^25 node -- and removed)
+  VAR_DMMA_32x32 = 18      // fp64 DMMA, one 32 x 32 tile with split-K over all SMs, two CTAs per SM: a few
+                           // peeled stem tails times the other stem (M, N <= 32 over K ~ 2^25)
 };
 
 // ---- single-operand descriptor (cotengra/contract.py:332-361) -------------

@@ -91,12 +91,13 @@ __device__ __forceinline__ double2 shfl_down_of(double2 v, int d) {
 // log10(factor) over the nodes, formed once per slice.
 struct StripCtx {
   double s;                 // 1/(fA fB): one multiply per component (0 when an operand is identically
-                            // zero: check_zero)
+                            // zero: check_zero); 1 when the host pre-scaled the small operand instead
   double sb;                // second factor, only used when the product 1/fA * 1/fB leaves the double range
   float sf;                 // s as a float when it is a normal float (single precision kernels), else 0
-  double run;               // largest |value| this thread has stored
+  double run2;              // largest |value|^2 this thread has stored (the common, cheap path)
+  double runh;              // largest |value| among values whose square leaves the double range
   unsigned long long* fc;   // factor slot of C (nullptr: the caller measures C separately)
-  bool scale, two;
+  bool on, scale, two;
 };
 __device__ __forceinline__ StripCtx strip_begin(const int64_t* __restrict__ D) {
   StripCtx c;
@@ -104,7 +105,8 @@ __device__ __forceinline__ StripCtx strip_begin(const int64_t* __restrict__ D) {
   const double* pb = reinterpret_cast<const double*>(D[W_SCALE_B]);
   c.scale = pa != nullptr;
   c.fc = reinterpret_cast<unsigned long long*>(D[W_FACTOR_C]);
-  c.run = 0.0;
+  c.on = c.scale || c.fc != nullptr;
+  c.run2 = c.runh = 0.0;
   c.s = c.sb = 1.0;
   c.sf = 1.f;
   c.two = false;
@@ -117,49 +119,49 @@ __device__ __forceinline__ StripCtx strip_begin(const int64_t* __restrict__ D) {
     c.s = c.two ? sa : prod;
     c.sb = c.two ? sb : 1.0;
     const double ap = fabs(prod);
-    c.sf = (!c.two && (ap == 0.0 || (ap > 1e-30 && ap < 1e30))) ? (float)prod : 0.f;
     // (sf == 0 with s != 0: single precision kernels fall back to the double multiply)
+    c.sf = (!c.two && (ap == 0.0 || (ap > 1e-30 && ap < 1e30))) ? (float)prod : 0.f;
   }
   return c;
 }
+// max |v| as the maximum of re^2 + im^2 (two FMAs, no branch in the common case; the square root
+// is taken once at the end) -- values whose square would underflow or overflow, and NaNs, take the
+// hypot path and keep their own maximum, so that magnitudes down to the denormals survive.
 __device__ __forceinline__ void strip_track(StripCtx& c, double re, double im) {
-  // max of hypot(re, im) without a hypot per element: only candidates that can beat the
-  // running maximum pay for it (no squaring: |v| down to the denormals keeps its value)
-  // (|re| + |im| >= hypot, and it is NaN when either part is: NaN is sticky, as in numpy's max)
-  if (c.run != c.run) return;
-  const double a = fabs(re) + fabs(im);
-  if (!(a <= c.run)) {
-    const double h = hypot(re, im);
-    c.run = (h != h) ? h : fmax(c.run, h);
+  const double q = fma(re, re, im * im);
+  if (q >= 1e-280 && q <= 1e300) {
+    c.run2 = fmax(c.run2, q);
+  } else if (!(re == 0.0 && im == 0.0)) {
+    const double h = hypot(re, im);                          // tiny, huge or NaN
+    c.runh = (h != h || c.runh != c.runh) ? __longlong_as_double(0x7ff8000000000000LL) : fmax(c.runh, h);
   }
 }
+// single precision: the squares of floats are exact and in range as doubles
 __device__ __forceinline__ void strip_track_f(StripCtx& c, float re, float im) {
-  // single precision: the cheap test in float (exact: a sum of two non-negative floats rounded
-  // up or down still bounds nothing wrongly -- the test is only a filter, hypot decides)
-  const float a = fabsf(re) + fabsf(im);
-  if (!((double)a * 0.999999 <= c.run)) strip_track(c, (double)re, (double)im);
+  const double q = fma((double)re, (double)re, (double)im * (double)im);
+  c.run2 = (q != q) ? q : fmax(c.run2, q);  // NaN sticks
 }
 __device__ __forceinline__ double strip_mul(const StripCtx& c, double v) { return c.two ? v * c.s * c.sb : v * c.s; }
 __device__ __forceinline__ float strip_mul(const StripCtx& c, float v) {
   return (c.sf != 0.f || c.s == 0.0) ? v * c.sf : (float)strip_mul(c, (double)v);
 }
 __device__ __forceinline__ float strip_apply(StripCtx& c, float v) {
-  const float r = strip_mul(c, v);
+  const float r = c.scale ? strip_mul(c, v) : v;
   strip_track_f(c, r, 0.f);
   return r;
 }
 __device__ __forceinline__ double strip_apply(StripCtx& c, double v) {
-  const double r = strip_mul(c, v);
+  const double r = c.scale ? strip_mul(c, v) : v;
   strip_track(c, r, 0.0);
   return r;
 }
 __device__ __forceinline__ float2 strip_apply(StripCtx& c, float2 v) {
-  const float2 r = make_float2(strip_mul(c, v.x), strip_mul(c, v.y));
+  const float2 r = c.scale ? make_float2(strip_mul(c, v.x), strip_mul(c, v.y)) : v;
   strip_track_f(c, r.x, r.y);
   return r;
 }
 __device__ __forceinline__ double2 strip_apply(StripCtx& c, double2 v) {
-  const double2 r = make_double2(strip_mul(c, v.x), strip_mul(c, v.y));
+  const double2 r = c.scale ? make_double2(strip_mul(c, v.x), strip_mul(c, v.y)) : v;
   strip_track(c, r.x, r.y);
   return r;
 }
@@ -167,7 +169,9 @@ __device__ __forceinline__ double2 strip_apply(StripCtx& c, double2 v) {
 // their bit patterns, NaN (sign clear) above everything -- it propagates like the reference's
 __device__ __forceinline__ void strip_end(const StripCtx& c) {
   if (c.fc == nullptr) return;
-  unsigned long long bits = (unsigned long long)__double_as_longlong(c.run != c.run ? __longlong_as_double(0x7ff8000000000000LL) : c.run);
+  const double m = fmax(sqrt(c.run2), c.runh);
+  const bool nan = c.run2 != c.run2 || c.runh != c.runh;
+  unsigned long long bits = (unsigned long long)__double_as_longlong(nan ? __longlong_as_double(0x7ff8000000000000LL) : m);
 #pragma unroll
   for (int d = 16; d > 0; d >>= 1) {
     const unsigned long long o = __shfl_xor_sync(0xffffffffu, bits, d);
@@ -564,7 +568,6 @@ struct DmmaPolicy {
 #include "rowstream.cuh"
 #include "dmmastream.cuh"
 #include "dotstream.cuh"
-#include "dotdmma.cuh"
 #include "tc05_policy.cuh"
 #include "gett_ws.cuh"
 #include "tc05_kernel.cuh"
@@ -672,6 +675,28 @@ __global__ void add_chunk_kernel(const int64_t* __restrict__ D, T* __restrict__ 
 __global__ void commit_exponent_kernel(double* __restrict__ E, const double* __restrict__ es) {
   *E = fmax(*E, *es);
 }
+// strip_exponent, small operand pre-scaled: dst = src / (fA fB) over the whole underlying buffer of
+// the node's small operand (a few KB on a contraction stem), so that the big kernel's epilogue
+// only has to track max|C| -- two multiplies per output element of a 16 GiB result are not free
+// on the fp64 pipe the DMMAs run on.
+// v * sa * sb with the intermediate kept in double (sa alone may leave the float range)
+__device__ __forceinline__ float scale2_of(float v, double sa, double sb) { return (float)((double)v * sa * sb); }
+__device__ __forceinline__ double scale2_of(double v, double sa, double sb) { return v * sa * sb; }
+__device__ __forceinline__ float2 scale2_of(float2 v, double sa, double sb) {
+  return make_float2((float)((double)v.x * sa * sb), (float)((double)v.y * sa * sb));
+}
+__device__ __forceinline__ double2 scale2_of(double2 v, double sa, double sb) {
+  return make_double2(v.x * sa * sb, v.y * sa * sb);
+}
+template <typename T>
+__global__ void scale_copy_kernel(const T* __restrict__ src, T* __restrict__ dst, long long n,
+                                  const double* __restrict__ fa, const double* __restrict__ fb) {
+  const double a = *fa, b = *fb;
+  const double sa = a != 0.0 ? 1.0 / a : 0.0, sb = b != 0.0 ? 1.0 / b : 0.0;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    dst[i] = scale2_of(src[i], sa, sb);
+}
+
 // fused strip_exponent bookkeeping: factor slots of the listed tensors back to zero
 __global__ void reset_slots_kernel(double* __restrict__ f, const int* __restrict__ list, int n) {
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) f[list[i]] = 0.0;

@@ -446,7 +446,7 @@ gett_kernel(const int64_t* __restrict__ D, const T* __restrict__ A, const T* __r
       // and the warps sat in instruction-fetch stalls (ncu: 42 % of the epilogue samples of a
       // K=16 node were no_inst, the epilogue 30 % of the consumers' time).
       T* const ctile = C + baseC;
-      if (sctx.scale && pair_ok && m_valid == MT && n_valid == NT) {
+      if (sctx.on && pair_ok && m_valid == MT && n_valid == NT) {
         // strip_exponent, full tile with 256-bit stores: scale by 1/(fA fB), record max|C|
         P::epilogue(
             acc, scratch, [&](int r, int c, T v) { ctile[offMC[r] + offNC[c]] = strip_apply(sctx, v); },
@@ -455,7 +455,7 @@ gett_kernel(const int64_t* __restrict__ D, const T* __restrict__ A, const T* __r
               store_pair_of(ctile + offMC[r] + offNC[c], w0, w1);
             },
             true, n_valid);
-      } else if (sctx.scale) {
+      } else if (sctx.on) {
         // ... every other store mode (split-K partial sums are only scaled: fc is null and the
         // host measures C afterwards)
         P::epilogue(

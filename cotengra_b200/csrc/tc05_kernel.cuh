@@ -478,7 +478,7 @@ tc05_kernel(const int64_t* __restrict__ D, const float2* __restrict__ A, const f
         asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
 #pragma unroll
         for (int i = 0; i < 32; ++i) v[i] = __float_as_uint(__uint_as_float(v[i]) + __uint_as_float(u[i]));
-        if (sctx.scale) {
+        if (sctx.on) {
 #pragma unroll
           for (int i = 0; i < 32; i += 2) {
             const float2 z = strip_apply(sctx, make_float2(__uint_as_float(v[i]), __uint_as_float(v[i + 1])));

@@ -201,6 +201,7 @@ class ExecPlan:
             t = _T([full_shape[k] for k in keep], [fs[k] for k in keep], 0,
                    variant=any(ix in sliced_pos for ix in term))
             t.input_index = i
+            t.nbytes = self.input_nbytes[-1]  # the whole (unsliced) array: strip_exponent copies it scaled
             for k, ix in enumerate(term):
                 if ix in sliced_pos:
                     t.slice_pos.append(sliced_pos[ix])

@@ -68,10 +68,10 @@ def node_time(dtype, B, M, N, K, elems):
         if K >= 1 << 20:
             return _LAUNCH + nbytes / r["dot"]      # dot-stream kernels
         return _LAUNCH + nbytes / 2.5e12 + flops / 2e12
-    if dtype == "complex128" and M <= 32 and N <= 32 and B == 1 and K >= 1 << 20:
-        # DMMA dot kernel: fragments padded to 16 x 16 or 32 x 32
-        pad = 16 if (M <= 16 and N <= 16) else 32
-        return _LAUNCH + max(nbytes / 6.0e12, 8.0 * pad * pad * K / 30e12)
+    if dtype in ("complex128", "float64") and M <= 32 and N <= 32 and B == 1 and K >= 1 << 14:
+        # one 32 x 32 DMMA tile, split-K over two CTAs per SM (measured on M = N = 32, K = 2^25:
+        # 3.4 TB/s, 27 TFLOP/s)
+        return _LAUNCH + max(nbytes / 3.6e12, r["flop"] * 32.0 * 32.0 * K / 28e12)
     if K >= 1 << 12 and (M < 64 or M * N <= 1 << 14):
         # a small result over a long contracted range and no dot-stream kernel for it: a handful
         # of (mostly empty) tensor tiles with split-K atomics -- far from either roofline

@@ -24,7 +24,6 @@ own planners (tests/test_lowering.py).
 from __future__ import annotations
 
 import math
-import os
 from dataclasses import dataclass, field
 
 import numpy as np
@@ -61,7 +60,7 @@ VAR_SIMT_64x64, VAR_KRED, VAR_DMMA_128x64, VAR_DMMA_64x128, VAR_DMMA_256x32 = 0,
 VAR_DMMA_256x16, VAR_ROW_128x8, VAR_ROW_256x4, VAR_ROWSTREAM = 5, 6, 7, 8
 VAR_TC05_128x64, VAR_TC05_128x32, VAR_TC05_128x16 = 9, 10, 11
 VAR_DMMA3M_128x32, VAR_DMMA3M_256x16, VAR_DMMASTREAM, VAR_DOTSTREAM, VAR_DOTSTREAM4 = 12, 13, 14, 15, 16
-VAR_DOTDMMA, VAR_DMMA_32x32 = 17, 18
+VAR_DMMA_32x32 = 18
 DMMASTREAM_MAX_N = 16  # the kernel takes N <= 32, but at N = 32 the staged 256x32 policy is faster (31.8 vs 26 TFLOP/s)
 TC05_VARIANTS = (VAR_TC05_128x64, VAR_TC05_128x32, VAR_TC05_128x16)
 # (MT, NT, KT) of every kernel variant -- must match ctg_b200.cu's dispatch
@@ -83,7 +82,6 @@ VARIANT_TILES = {
     VAR_DMMASTREAM: (256, 32, 64),
     VAR_DOTSTREAM: (1, 1, 2048),
     VAR_DOTSTREAM4: (4, 4, 1024),
-    VAR_DOTDMMA: (32, 32, 128),
     VAR_DMMA_32x32: (32, 32, 32),
 }
 
@@ -336,11 +334,11 @@ def choose_variant(dtype, B, M, N, K, allow_dmma=True, allow_stream=True, allow_
         return VAR_DOTSTREAM
     if M <= 4 and N <= 4 and B == 1 and K >= 1 << 20 and allow_stream:
         return VAR_DOTSTREAM4  # a stem tail peeled over the final inner product (fusion.py)
-    if (dtype == "complex128" and allow_dmma and allow_stream and M <= 32 and N <= 32 and B == 1
-            and K >= 1 << 20):
-        # the same with a few more peeled tensors: DMMA fragments from global (DOTDMMA) or one staged
-        # 32 x 32 tile with split-K over all SMs (CTGB_DOT_VARIANT is a measurement knob)
-        return int(os.environ.get("CTGB_DOT_VARIANT", VAR_DOTDMMA))
+    if (dtype in ("complex128", "float64") and allow_dmma and M <= 32 and N <= 32 and M * N >= 4 and B == 1
+            and K >= 1 << 14):
+        # the same with a few more peeled tensors (fusion.py): ONE 32 x 32 fp64 tensor-core tile,
+        # the contracted range split over two CTAs per SM
+        return VAR_DMMA_32x32
     if M == 1 and N == 1 and B == 1 and K >= 8192:
         return VAR_KRED
     if N <= 8 and K <= 8 and B == 1 and 64 <= M < 1 << 32 and allow_stream:
@@ -411,6 +409,8 @@ def build_pair_desc(dims: PairDims, dtype, accumulate=False, sm_count=148,
         if not ok:
             variant = VAR_ROW_256x4 if N <= 4 else VAR_ROW_128x8
     MT, NT, KT = VARIANT_TILES[variant]
+    if variant == VAR_DOTSTREAM4 and DTYPE_SIZES[dtype] < 16:
+        KT = 2048  # 8 k per thread for the narrower element types (csrc/dotstream.cuh dot4_u)
 
     if variant in TC05_VARIANTS:
         # tcgen05: every thread of the epilogue owns a whole row, so the rows of a tile need
@@ -523,14 +523,6 @@ def build_pair_desc(dims: PairDims, dtype, accumulate=False, sm_count=148,
                                      or pm is not None or pn is not None
                                      or (pk is not None and pk[1] % pk[2] != 0)
                                      or not (accumulate or c_dense_elems == M * N)):
-        return build_pair_desc(dims, dtype, accumulate=accumulate, sm_count=sm_count, variant=VAR_SIMT_64x64,
-                               allow_dmma=allow_dmma, c_dense_elems=c_dense_elems, force_splitk=force_splitk)
-    if variant == VAR_DOTDMMA and (not (dtype == "complex128" and M <= 32 and N <= 32 and B == 1) or len(gk) > 40
-                                  or steps_k >= 1 << 31 or pm is not None or pn is not None
-                                  or (pk is not None and pk[1] % pk[2] != 0) or KTa != KT or not (accumulate or c_dense_elems == M * N)
-                                  # (32-bit tile-local offsets in the kernel)
-                                  or sum((d[0] - 1) * abs(d[1]) for d in tm + tk) >= 1 << 32
-                                  or sum((d[0] - 1) * abs(d[1]) for d in tn) + sum((d[0] - 1) * abs(d[2]) for d in tk) >= 1 << 32):
         return build_pair_desc(dims, dtype, accumulate=accumulate, sm_count=sm_count, variant=VAR_SIMT_64x64,
                                allow_dmma=allow_dmma, c_dense_elems=c_dense_elems, force_splitk=force_splitk)
     if variant == VAR_DMMASTREAM and (pn is not None or pk is not None or (pm is not None and pm[1] % pm[2] != 0)):

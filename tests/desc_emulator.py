@@ -43,6 +43,8 @@ def emulate_pair(W, A, B, C):
     tiles_m, tiles_n, tiles_b, steps_k = (int(W[i]) for i in (L.W_TILES_M, L.W_TILES_N, L.W_TILES_B, L.W_STEPS_K))
     splitk = int(W[L.W_SPLITK])
     MT, NT, KT = L.VARIANT_TILES[int(W[L.W_VARIANT])]
+    if int(W[L.W_VARIANT]) == L.VAR_DOTSTREAM4 and int(W[L.W_DTYPE]) != L.DTYPE_CODES["complex128"]:
+        KT = 2048
     assert MTa <= MT and NTa <= NT and KTa <= KT, (MTa, NTa, KTa, MT, NT, KT)
     accumulate = bool(W[L.W_FLAGS] & 1)
     tm = _rows(W, L.OFF_TM, n_tm, 3)

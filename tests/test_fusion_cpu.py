@@ -89,7 +89,7 @@ def test_sycamore_stem_moves_fewer_bytes():
     from cotengra_b200 import lowering as L
 
     variants = [nd["plan"].variant for nd in p1.nodes if nd["kind"] == 0 and not nd["invariant"]]
-    assert L.VAR_DOTDMMA in variants or L.VAR_DOTSTREAM4 in variants
+    assert L.VAR_DMMA_32x32 in variants or L.VAR_DOTSTREAM4 in variants
     # estimated time drops by more than 10 %
     def est(p):
         return sum(node_time("complex128", *nd["sizes"], sum(math.prod(x.shape) for x in (nd["a"], nd["b"], nd["c"])))

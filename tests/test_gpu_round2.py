@@ -130,8 +130,8 @@ def test_dotstream4_pair(dtype, mn):
 
 
 @pytest.mark.parametrize("mn", [(32, 32), (16, 32), (8, 8), (5, 20), (32, 4), (16, 16)])
-def test_dotdmma_pair(mn):
-    """complex128, M, N <= 32 over K = 2^21: DMMA fragments straight from global memory
+def test_dmma_32x32_splitk_pair(mn):
+    """complex128, M, N <= 32 over K = 2^21: one 32 x 32 DMMA tile with split-K over all SMs
     (peeled stem tails, fusion.py)."""
     M, N = mn
     shape_a = (8, 64, M, 4, 1024)          # a, b, m, c, d
@@ -139,7 +139,7 @@ def test_dotdmma_pair(mn):
     a, b = make_arrays([shape_a, shape_b], "complex128", seed=9)
     dims = L.classify_pair("abmcd", shape_a, "dncab", shape_b, "mn")
     plan = L.build_pair_desc(dims, "complex128", c_dense_elems=M * N)
-    assert plan.variant == (L.VAR_DOTSTREAM4 if max(M, N) <= 4 else L.VAR_DOTDMMA)
+    assert plan.variant == (L.VAR_DOTSTREAM4 if max(M, N) <= 4 else L.VAR_DMMA_32x32)
     got = cb.einsum("abmcd,dncab->mn", a, b)
     want = np.einsum("abmcd,dncab->mn", a, b)
     assert rel_err(got, want) < 1e-10

@@ -231,3 +231,27 @@ def test_tcgen05_descriptor_properties():
             want = np.einsum("".join(ta) + "," + "".join(tb) + "->" + "".join(out), a, b)
             assert rel_err(got, want) < 1e-5
     assert seen_bulk >= 10 and seen_gather >= 3, (seen_bulk, seen_gather)
+
+
+@pytest.mark.parametrize("variant,dtype,mn", [
+    (L.VAR_DOTSTREAM4, "complex128", (4, 3)), (L.VAR_DOTSTREAM4, "complex64", (2, 4)),
+    (L.VAR_DMMA_32x32, "complex128", (32, 20)), (L.VAR_DMMA_32x32, "complex128", (32, 32)),
+    (L.VAR_DMMA_32x32, "float64", (24, 32)),
+])
+def test_small_result_long_k_descriptors(variant, dtype, mn):
+    """The dot-type variants stem fusion produces (a small kept space on both operands over a
+    long, permuted contracted space): descriptor addressing through the emulator vs einsum."""
+    from tests.desc_emulator import emulate_pair
+
+    M, N = mn
+    shape_a = (4, 16, M, 2, 64)        # a, b, m, c, d     K = 4*16*2*64 = 8192
+    shape_b = (64, N, 2, 4, 16)        # d, n, c, a, b
+    a, b = make_arrays([shape_a, shape_b], dtype, seed=2)
+    dims = L.classify_pair("abmcd", shape_a, "dncab", shape_b, "mn")
+    plan = L.build_pair_desc(dims, dtype, c_dense_elems=M * N, variant=variant, force_splitk=4 if variant == L.VAR_DMMA_32x32 else None)
+    assert plan.variant == variant
+    x, y = (b, a) if plan.swapped else (a, b)
+    out = np.full(M * N, 7, dtype=dtype)
+    emulate_pair(plan.words, x.reshape(-1), y.reshape(-1), out)
+    want = np.einsum("abmcd,dncab->mn", a, b)
+    assert rel_err(out.reshape(M, N), want) < (1e-12 if "128" in dtype or dtype == "float64" else 1e-5)
