@@ -624,6 +624,8 @@ int ctgb_plan_create(const ctgb_plan_desc* pd, ctgb_plan** out) {
     if (pd->strip_exponent && n.kind == 0) {
       const int64_t* w = n.desc;
       q.measure_after = w[W_SPLITK] > 1 || w[W_VARIANT] == VAR_DOTSTREAM || w[W_VARIANT] == VAR_DOTSTREAM4;
+      // (the block-reduction epilogue of KRED runs once: its result is measured afterwards as well)
+      q.measure_after |= w[W_VARIANT] == VAR_KRED;
     }
     if (!n.invariant) per_slice += 1 + q.measure_after + (pd->strip_exponent && n.kind == 0 ? 1 : 0);
   }

@@ -170,6 +170,28 @@ dmmastream_kernel(const int64_t* __restrict__ D, const double2* __restrict__ A, 
             if (j < n8s) dmma8x8x4(im[i][j][0], im[i][j][1], a[i][k4].y, b[j].x);
       }
     }
+    if constexpr (STRIP) {
+      if (!sctx.scale) {
+        // max|C|: integer scan over the accumulators, then (rarely) the values (see gett_ws.cuh)
+        int hmax = 0;
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+          for (int j = 0; j < NJ; ++j)
+#pragma unroll
+            for (int e = 0; e < 2; ++e)
+              hmax = max(hmax, max(strip_hi(re[i][j][e]), strip_hi(im[i][j][e])));
+        if (strip_hot<double2>(sctx, hmax)) {
+#pragma unroll
+          for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int j = 0; j < NJ; ++j)
+#pragma unroll
+              for (int e = 0; e < 2; ++e)
+                if (live[i] && j * 8 + fc + e < N) strip_track(sctx, re[i][j][e], im[i][j][e]);
+        }
+      }
+    }
     // a lane owns columns (fc, fc+1) of fragment j in row i*8 + frow
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
@@ -181,8 +203,10 @@ dmmastream_kernel(const int64_t* __restrict__ D, const double2* __restrict__ A, 
         if (c >= N) continue;
         double2 v0 = make_double2(re[i][j][0], im[i][j][0]), v1 = make_double2(re[i][j][1], im[i][j][1]);
         if constexpr (STRIP) {
-          v0 = strip_apply(sctx, v0);
-          if (c + 1 < N) v1 = strip_apply(sctx, v1);
+          if (sctx.scale) {
+            v0 = strip_apply(sctx, v0);
+            if (c + 1 < N) v1 = strip_apply(sctx, v1);
+          }
         }
         if (pair_ok) {
           store_pair_of(crow + s_cnoff[c], v0, v1);

@@ -89,13 +89,17 @@ __device__ __forceinline__ double2 shfl_down_of(double2 v, int d) {
 // accumulators by 1/(factor_A * factor_B) in the epilogue -- the same numbers the reference
 // forms, (A/fA)(B/fB), since the product is bilinear -- and the exponent is the sum of
 // log10(factor) over the nodes, formed once per slice.
+struct StripMax {
+  double run2;              // largest |value|^2 this thread has stored (the common path)
+  double runh;              // largest |value| among values whose square leaves the double range
+  int thr, thrf;            // integer filters: high word of (max/sqrt 2) as a double / its bits as a float
+};
 struct StripCtx {
   double s;                 // 1/(fA fB): one multiply per component (0 when an operand is identically
-                            // zero: check_zero); 1 when the host pre-scaled the small operand instead
+                            // zero: check_zero); unused when the host pre-scaled the small operand
   double sb;                // second factor, only used when the product 1/fA * 1/fB leaves the double range
   float sf;                 // s as a float when it is a normal float (single precision kernels), else 0
-  double run2;              // largest |value|^2 this thread has stored (the common, cheap path)
-  double runh;              // largest |value| among values whose square leaves the double range
+  StripMax m;
   unsigned long long* fc;   // factor slot of C (nullptr: the caller measures C separately)
   bool on, scale, two;
 };
@@ -106,7 +110,8 @@ __device__ __forceinline__ StripCtx strip_begin(const int64_t* __restrict__ D) {
   c.scale = pa != nullptr;
   c.fc = reinterpret_cast<unsigned long long*>(D[W_FACTOR_C]);
   c.on = c.scale || c.fc != nullptr;
-  c.run2 = c.runh = 0.0;
+  c.m.run2 = c.m.runh = 0.0;
+  c.m.thr = c.m.thrf = 0;
   c.s = c.sb = 1.0;
   c.sf = 1.f;
   c.two = false;
@@ -124,23 +129,57 @@ __device__ __forceinline__ StripCtx strip_begin(const int64_t* __restrict__ D) {
   }
   return c;
 }
-// max |v| as the maximum of re^2 + im^2 (two FMAs, no branch in the common case; the square root
-// is taken once at the end) -- values whose square would underflow or overflow, and NaNs, take the
-// hypot path and keep their own maximum, so that magnitudes down to the denormals survive.
-__device__ __forceinline__ void strip_track(StripCtx& c, double re, double im) {
+// max |v|: INLINE there is only an integer filter -- non-negative floating-point numbers order like
+// their bit patterns, so an element whose larger component lies below (current maximum)/sqrt(2) is
+// dismissed with four ALU instructions and touches neither the fp64 pipe the DMMAs run on nor the
+// instruction cache (with the arithmetic inlined at each of the 32-64 store sites of an unrolled
+// epilogue the DMMA nodes lost 18 %, the tcgen05 nodes 60 %: instruction fetch).  The rare candidates
+// call ONE out-of-line routine: re^2 + im^2 against the running maximum of squares (square root taken
+// once at the end); squares that would leave the double range, and NaNs, take a hypot path with its own
+// maximum, so that magnitudes down to the denormals survive.
+__device__ __noinline__ StripMax strip_track_slow(StripMax m, double re, double im) {
   const double q = fma(re, re, im * im);
   if (q >= 1e-280 && q <= 1e300) {
-    c.run2 = fmax(c.run2, q);
+    if (!(q > m.run2)) return m;
+    m.run2 = q;
   } else if (!(re == 0.0 && im == 0.0)) {
-    const double h = hypot(re, im);                          // tiny, huge or NaN
-    c.runh = (h != h || c.runh != c.runh) ? __longlong_as_double(0x7ff8000000000000LL) : fmax(c.runh, h);
+    const double hy = hypot(re, im);                         // tiny, huge or NaN
+    m.runh = (hy != hy || m.runh != m.runh) ? __longlong_as_double(0x7ff8000000000000LL) : fmax(m.runh, hy);
+  } else {
+    return m;
   }
+  // high word of max/sqrt(2), rounded down: everything strictly below it cannot raise the maximum
+  const double t = fmax(sqrt(m.run2), m.runh) * 0.70710678118654746;
+  m.thr = (t == t) ? __double2hiint(t) : 0;
+  m.thrf = (t == t && t < 3e38) ? __float_as_int((float)t * 0.999999f) : 0;
+  return m;
 }
-// single precision: the squares of floats are exact and in range as doubles
+__device__ __forceinline__ void strip_track(StripCtx& c, double re, double im) {
+  const int h = max(__double2hiint(re) & 0x7fffffff, __double2hiint(im) & 0x7fffffff);
+  if (h >= c.m.thr) c.m = strip_track_slow(c.m, re, im);
+}
 __device__ __forceinline__ void strip_track_f(StripCtx& c, float re, float im) {
-  const double q = fma((double)re, (double)re, (double)im * (double)im);
-  c.run2 = (q != q) ? q : fmax(c.run2, q);  // NaN sticks
+  const int h = max(__float_as_int(re) & 0x7fffffff, __float_as_int(im) & 0x7fffffff);
+  if (h >= c.m.thrf) c.m = strip_track_slow(c.m, (double)re, (double)im);
 }
+// branch-free part of the filter, for a scan over a whole tile of accumulators before they are
+// stored: the bit pattern of the largest component, sign stripped (two integer ops per component)
+__device__ __forceinline__ int strip_hi(float v) { return __float_as_int(v) & 0x7fffffff; }
+__device__ __forceinline__ int strip_hi(double v) { return __double2hiint(v) & 0x7fffffff; }
+__device__ __forceinline__ int strip_hi(float2 v) { return max(strip_hi(v.x), strip_hi(v.y)); }
+__device__ __forceinline__ int strip_hi(double2 v) { return max(strip_hi(v.x), strip_hi(v.y)); }
+template <typename T> struct StripSingle { static constexpr bool value = false; };
+template <> struct StripSingle<float> { static constexpr bool value = true; };
+template <> struct StripSingle<float2> { static constexpr bool value = true; };
+// can anything with this (sign-stripped) leading bit pattern raise the running maximum?
+template <typename T>
+__device__ __forceinline__ bool strip_hot(const StripCtx& c, int hmax) {
+  return hmax >= (StripSingle<T>::value ? c.m.thrf : c.m.thr);
+}
+__device__ __forceinline__ void strip_note(StripCtx& c, float v) { strip_track_f(c, v, 0.f); }
+__device__ __forceinline__ void strip_note(StripCtx& c, double v) { strip_track(c, v, 0.0); }
+__device__ __forceinline__ void strip_note(StripCtx& c, float2 v) { strip_track_f(c, v.x, v.y); }
+__device__ __forceinline__ void strip_note(StripCtx& c, double2 v) { strip_track(c, v.x, v.y); }
 __device__ __forceinline__ double strip_mul(const StripCtx& c, double v) { return c.two ? v * c.s * c.sb : v * c.s; }
 __device__ __forceinline__ float strip_mul(const StripCtx& c, float v) {
   return (c.sf != 0.f || c.s == 0.0) ? v * c.sf : (float)strip_mul(c, (double)v);
@@ -169,8 +208,8 @@ __device__ __forceinline__ double2 strip_apply(StripCtx& c, double2 v) {
 // their bit patterns, NaN (sign clear) above everything -- it propagates like the reference's
 __device__ __forceinline__ void strip_end(const StripCtx& c) {
   if (c.fc == nullptr) return;
-  const double m = fmax(sqrt(c.run2), c.runh);
-  const bool nan = c.run2 != c.run2 || c.runh != c.runh;
+  const double m = fmax(sqrt(c.m.run2), c.m.runh);
+  const bool nan = c.m.run2 != c.m.run2 || c.m.runh != c.m.runh;
   unsigned long long bits = (unsigned long long)__double_as_longlong(nan ? __longlong_as_double(0x7ff8000000000000LL) : m);
 #pragma unroll
   for (int d = 16; d > 0; d >>= 1) {
@@ -224,6 +263,8 @@ struct SimtPolicy {
   static constexpr int CONSUMER_REGS = 0, PRODUCER_REGS = 0;
   static constexpr bool HAS_BCACHE = false;
   static constexpr int MIN_BLOCKS = sizeof(T) == 16 ? 1 : 2;
+  // strip_exponent: may the epilogue be traversed more than once (scan for max|C|, then store)?
+  static constexpr bool SCAN_OK = true;
   struct Acc {
     T v[TM][TN];
   };
@@ -251,6 +292,7 @@ struct SimtPolicy {
         for (int j = 0; j < TN; ++j) mac(acc.v[i][j], a[i], b[j]);
     }
   }
+  __device__ static __forceinline__ void finalize(Acc&) {}
   template <typename F, typename F2>
   __device__ static __forceinline__ void epilogue(Acc& acc, T* scratch, F&& store, F2&& store_pair, bool pair_ok,
                                                   int ncols) {
@@ -274,6 +316,8 @@ struct KredPolicy {
   static constexpr int CONSUMER_REGS = 0, PRODUCER_REGS = 0;
   static constexpr bool HAS_BCACHE = false;
   static constexpr int MIN_BLOCKS = 2;
+  // strip_exponent: may the epilogue be traversed more than once (scan for max|C|, then store)?
+  static constexpr bool SCAN_OK = false;
   struct Acc {
     T v[MT][NT];
   };
@@ -300,6 +344,7 @@ struct KredPolicy {
         for (int j = 0; j < NT; ++j) mac(acc.v[i][j], a[i], b[j]);
     }
   }
+  __device__ static __forceinline__ void finalize(Acc&) {}
   template <typename F, typename F2>
   __device__ static __forceinline__ void epilogue(Acc& acc, T* scratch, F&& store, F2&& store_pair, bool pair_ok,
                                                   int ncols) {
@@ -344,6 +389,8 @@ struct RowPolicy {
   struct BCache {
     T v[KT][NT];
   };
+  // strip_exponent: may the epilogue be traversed more than once (scan for max|C|, then store)?
+  static constexpr bool SCAN_OK = true;
   struct Acc {
     T v[2][NT];
   };
@@ -389,6 +436,7 @@ struct RowPolicy {
       }
     }
   }
+  __device__ static __forceinline__ void finalize(Acc&) {}
   template <typename F, typename F2>
   __device__ static __forceinline__ void epilogue(Acc& acc, T* scratch, F&& store, F2&& store_pair, bool pair_ok,
                                                   int ncols) {
@@ -443,6 +491,7 @@ struct DmmaPolicy {
   static constexpr bool HAS_BCACHE = false;
   static constexpr int MIN_BLOCKS = THREADS <= 128 ? 2 : 1;  // the 32 x 32 split-K policy: two CTAs per SM
   static_assert(KT % 4 == 0, "KT must be a multiple of the DMMA k");
+  static constexpr bool SCAN_OK = true;
   struct Acc {
     double re[FM][FN][2];
     double im[CPLX ? FM : 1][CPLX ? FN : 1][2];
@@ -527,6 +576,21 @@ struct DmmaPolicy {
       }
     }
   }
+  // once per tile, before the epilogue passes: 3M turns (P1, P2, P3) into (re, im)
+  __device__ static __forceinline__ void finalize(Acc& acc) {
+    if constexpr (M3) {
+#pragma unroll
+      for (int i = 0; i < FM; ++i)
+#pragma unroll
+        for (int j = 0; j < FN; ++j)
+#pragma unroll
+          for (int e = 0; e < 2; ++e) {
+            const double p1 = acc.re[i][j][e], p2 = acc.im[i][j][e];
+            acc.re[i][j][e] = p1 - p2;
+            acc.im[i][j][e] = acc.p3[i][j][e] - p1 - p2;
+          }
+    }
+  }
   template <typename F, typename F2>
   __device__ static __forceinline__ void epilogue(Acc& acc, T* scratch, F&& store, F2&& store_pair, bool pair_ok,
                                                   int ncols) {
@@ -539,14 +603,6 @@ struct DmmaPolicy {
       for (int j = 0; j < FN; ++j) {
         const int r = (wm * FM + i) * 8 + frow;
         const int c = (wn * FN + j) * 8 + fc;
-        if constexpr (M3) {
-#pragma unroll
-          for (int e = 0; e < 2; ++e) {
-            const double p1 = acc.re[i][j][e], p2 = acc.im[i][j][e];
-            acc.re[i][j][e] = p1 - p2;
-            acc.im[i][j][e] = acc.p3[i][j][e] - p1 - p2;
-          }
-        }
         if constexpr (CPLX) {
           // a lane owns two adjacent columns of the fragment: one 256-bit store
           if (pair_ok) {

@@ -446,18 +446,39 @@ gett_kernel(const int64_t* __restrict__ D, const T* __restrict__ A, const T* __r
       // and the warps sat in instruction-fetch stalls (ncu: 42 % of the epilogue samples of a
       // K=16 node were no_inst, the epilogue 30 % of the consumers' time).
       T* const ctile = C + baseC;
-      if (sctx.on && pair_ok && m_valid == MT && n_valid == NT) {
-        // strip_exponent, full tile with 256-bit stores: scale by 1/(fA fB), record max|C|
-        P::epilogue(
-            acc, scratch, [&](int r, int c, T v) { ctile[offMC[r] + offNC[c]] = strip_apply(sctx, v); },
-            [&](int r, int c, T v0, T v1) {
-              const T w0 = strip_apply(sctx, v0), w1 = strip_apply(sctx, v1);
-              store_pair_of(ctile + offMC[r] + offNC[c], w0, w1);
-            },
-            true, n_valid);
-      } else if (sctx.on) {
-        // ... every other store mode (split-K partial sums are only scaled: fc is null and the
-        // host measures C afterwards)
+      P::finalize(acc);
+      bool strip_store = false;
+      if (sctx.on) {
+        if (sctx.scale || !P::SCAN_OK) {
+          // both operands large (no pre-scaled copy of the small one): scale by 1/(fA fB) and track
+          // in the store pass itself (rare: dot-type nodes, whose results are tiny)
+          strip_store = true;
+        } else {
+          // strip_exponent, the usual case: max|C| of the tile.  A branch-free integer scan over the
+          // accumulators (two ALU ops per component) finds the leading bit pattern of the largest
+          // component; only if that can raise this thread's running maximum does the cold block look
+          // at the values themselves.  The stores below are the ordinary ones.
+          int hmax = 0;
+          P::epilogue(
+              acc, scratch, [&](int, int, T v) { hmax = max(hmax, strip_hi(v)); },
+              [&](int, int, T v0, T v1) { hmax = max(hmax, max(strip_hi(v0), strip_hi(v1))); }, pair_ok, n_valid);
+          if (strip_hot<T>(sctx, hmax)) {
+            P::epilogue(
+                acc, scratch,
+                [&](int r, int c, T v) {
+                  if (r < m_valid && c < n_valid) strip_note(sctx, v);
+                },
+                [&](int r, int c, T v0, T v1) {
+                  if (r < m_valid && c < n_valid) {
+                    strip_note(sctx, v0);
+                    strip_note(sctx, v1);
+                  }
+                },
+                pair_ok, n_valid);
+          }
+        }
+      }
+      if (strip_store) {
         P::epilogue(
             acc, scratch,
             [&](int r, int c, T v) {

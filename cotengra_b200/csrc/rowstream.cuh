@@ -163,9 +163,22 @@ rowstream_kernel(const int64_t* __restrict__ D, const T* __restrict__ A, const T
           }
         }
         if constexpr (STRIP) {
+          if (sctx.scale) {
 #pragma unroll
-          for (int c = 0; c < CH; ++c)
-            if (c0 + c < N) acc[c] = strip_apply(sctx, acc[c]);
+            for (int c = 0; c < CH; ++c)
+              if (c0 + c < N) acc[c] = strip_apply(sctx, acc[c]);
+          } else {
+            // integer scan, then (rarely) a look at the values: see gett_ws.cuh
+            int hmax = 0;
+#pragma unroll
+            for (int c = 0; c < CH; ++c)
+              if (c0 + c < N) hmax = max(hmax, strip_hi(acc[c]));
+            if (strip_hot<T>(sctx, hmax)) {
+#pragma unroll
+              for (int c = 0; c < CH; ++c)
+                if (c0 + c < N) strip_note(sctx, acc[c]);
+            }
+          }
         }
         bool done = false;
         if constexpr (sizeof(T) == 8) {

@@ -479,11 +479,22 @@ tc05_kernel(const int64_t* __restrict__ D, const float2* __restrict__ A, const f
 #pragma unroll
         for (int i = 0; i < 32; ++i) v[i] = __float_as_uint(__uint_as_float(v[i]) + __uint_as_float(u[i]));
         if (sctx.on) {
+          if (sctx.scale) {
 #pragma unroll
-          for (int i = 0; i < 32; i += 2) {
-            const float2 z = strip_apply(sctx, make_float2(__uint_as_float(v[i]), __uint_as_float(v[i + 1])));
-            v[i] = __float_as_uint(z.x);
-            v[i + 1] = __float_as_uint(z.y);
+            for (int i = 0; i < 32; i += 2) {
+              const float2 z = strip_apply(sctx, make_float2(__uint_as_float(v[i]), __uint_as_float(v[i + 1])));
+              v[i] = __float_as_uint(z.x);
+              v[i + 1] = __float_as_uint(z.y);
+            }
+          } else {
+            // max|C|: integer scan over the 32 words, then (rarely) the values (see gett_ws.cuh)
+            int hmax = 0;
+#pragma unroll
+            for (int i = 0; i < 32; ++i) hmax = max(hmax, (int)(v[i] & 0x7fffffffu));
+            if (strip_hot<float2>(sctx, hmax)) {
+#pragma unroll
+              for (int i = 0; i < 32; i += 2) strip_track_f(sctx, __uint_as_float(v[i]), __uint_as_float(v[i + 1]));
+            }
           }
         }
 #pragma unroll

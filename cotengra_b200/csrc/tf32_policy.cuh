@@ -46,6 +46,7 @@ struct Tf32Policy {
   static constexpr bool HAS_BCACHE = false;
   static constexpr int MIN_BLOCKS = 1;
   static_assert(KT % 8 == 0, "KT must be a multiple of the MMA k");
+  static constexpr bool SCAN_OK = true;
   struct Acc {
     float re[FM][FN][4];
     float im[CPLX ? FM : 1][CPLX ? FN : 1][4];
@@ -126,6 +127,7 @@ struct Tf32Policy {
       }
     }
   }
+  __device__ static __forceinline__ void finalize(Acc&) {}
   template <typename F, typename F2>
   __device__ static __forceinline__ void epilogue(Acc& acc, T* scratch, F&& store, F2&& store_pair, bool pair_ok,
                                                   int ncols) {

@@ -1,6 +1,6 @@
 """Standalone benchmark of the heaviest nodes of one Sycamore-m20 slice (dev tool).
 
-usage: python scripts/gpu_node_bench.py [dtype] [topk] [--ncu] [--rows] [--mnk=M,N,K]
+usage: python scripts/gpu_node_bench.py [dtype] [topk] [--ncu] [--rows] [--mnk=M,N,K] [--nofuse] [--variant=ID]
 Each selected node is launched alone through ctgb_contract_pair on dummy
 operands of the right size, timed with CUDA events; with --ncu one launch per
 node is bracketed by cudaProfilerStart/Stop (run under
@@ -23,8 +23,13 @@ rows_only = "--rows" in sys.argv
 mnk = next((tuple(int(x) for x in a.split("=")[1].split(",")) for a in sys.argv if a.startswith("--mnk=")), None)
 rec = next(r for r in load_json("sycamore_m20.json") if r["name"] == "sycamore_m20_appxB")
 spec = cb.TreeSpec(rec["inputs"], rec["output"], rec["size_dict"], rec["path"], decode_sliced(rec["sliced"]))
+if "--nofuse" not in sys.argv:
+    from cotengra_b200.fusion import fuse_stems
+
+    spec, _info = fuse_stems(spec, dtype)  # the plan the executor runs by default
+force = next((int(a.split("=")[1]) for a in sys.argv if a.startswith("--variant=")), None)
 plan = cb.ExecPlan(spec.contractions(), spec.inputs, spec.output, spec.size_dict, spec.sliced, dtype=dtype,
-                   sm_count=_lib.device_info()["sm_count"])
+                   sm_count=_lib.device_info()["sm_count"], variant=force)
 es = plan.esize
 nodes = [nd for nd in plan.nodes if nd["kind"] == 0 and not nd["invariant"]]
 if rows_only:

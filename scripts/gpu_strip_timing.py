@@ -34,6 +34,12 @@ for strip in (False, True):
     one = ex.contract_device(dev, begin=0, step=1, count=1)
     vals[strip] = (complex(one[0].reshape(-1)[0].item()) * 10.0 ** float(one[1].item())) if strip else complex(one.reshape(-1)[0].item())
     res[f"launches_per_slice_{strip}"] = ex.plan.launches_per_slice()
+    ex.plan.profile(True)
+    ex.contract_device(dev, begin=7, step=1, count=1)
+    torch.cuda.synchronize()
+    res[f"nodes_{strip}"] = [(nd["sizes"], int(nd["plan"].variant), t) for nd, t in zip(ex.plan.nodes, ex.plan.profile_read())
+                             if nd["kind"] == 0 and not nd["invariant"]]
+    ex.plan.profile(False)
     del ex
     torch.cuda.empty_cache()
 line = {"dtype": dtype, "slice_ms_plain": res[False], "slice_ms_strip_exponent": res[True],
@@ -42,3 +48,7 @@ line = {"dtype": dtype, "slice_ms_plain": res[False], "slice_ms_strip_exponent":
         "value_plain": [vals[False].real, vals[False].imag], "value_stripped": [vals[True].real, vals[True].imag],
         "rel_diff": abs(vals[True] - vals[False]) / abs(vals[False])}
 print(json.dumps(line))
+# the nodes that pay most for stripping
+rows = sorted(((b[2] - a[2], a[0], a[1], a[2], b[2]) for a, b in zip(res["nodes_False"], res["nodes_True"])), reverse=True)
+for d, sizes, var, t0, t1 in rows[:12]:
+    print(f"  +{d:6.2f} ms  {t0:7.2f} -> {t1:7.2f}  B,M,N,K={sizes} variant {var}", file=sys.stderr)
