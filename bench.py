@@ -1,7 +1,7 @@
 """bench.py -- Sycamore n53 m20 sliced-contraction throughput (BASELINE.json metric).
 
     python bench.py --gpus N --steps K --warmup W [--dtype complex128] [--impl reference]
-                    [--config m20|peps8x8|m10|m12] [--scaling weak|strong]
+                    [--config m20|peps8x8|m10|m10s|m12] [--scaling weak|strong]
 
 Default workload (config.workload): the reference's own benchmark structure
 ``examples/benchmarks/sycamore_n53_m20_s0_e0_pABCDCDAB.json`` (381 tensors, 754
@@ -49,6 +49,7 @@ METRICS = {
     "m20": "sycamore_n53_m20_sliced_contract_tflops",
     "peps8x8": "peps8x8_bond6_contract_tflops",
     "m10": "sycamore_n53_m10_amplitude_tflops",
+    "m10s": "sycamore_n53_m10_rank_simplified_amplitude_tflops",
     "m12": "sycamore_n53_m12_256slices_tflops",
 }
 UNIT = "TFLOP/s"

@@ -33,6 +33,7 @@ EXPORTS = (
     "ctgb_plan_execute",
     "ctgb_plan_execute_host",
     "ctgb_launch_count",
+    "ctgb_tensor_map_launches",
     "ctgb_plan_profile",
     "ctgb_plan_profile_read",
     "ctgb_probe_fp64_peaks",
@@ -104,6 +105,7 @@ def load():
             raise ImportError(f"{LIB_PATH} does not export {name}")
     lib.ctgb_last_error.restype = C.c_char_p
     lib.ctgb_launch_count.restype = C.c_int64
+    lib.ctgb_tensor_map_launches.restype = C.c_int64
     lib.ctgb_plan_workspace_bytes.restype = C.c_size_t
     lib.ctgb_plan_workspace_bytes.argtypes = [C.c_void_p]
     lib.ctgb_plan_launches_per_slice.restype = C.c_int64
@@ -161,3 +163,8 @@ def probe_fp64_peaks(stream=0):
 
 def launch_count() -> int:
     return int(load().ctgb_launch_count())
+
+
+def tensor_map_launches() -> int:
+    """tcgen05 launches so far whose A tiles were fetched by tensor-map TMA."""
+    return int(load().ctgb_tensor_map_launches())

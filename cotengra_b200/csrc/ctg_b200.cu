@@ -7,9 +7,11 @@
 //   slice_key / slice_arrays ............. cotengra/core.py:3775-3819
 //   gather_slices (sum and stack) ........ cotengra/core.py:3825-3882
 //   contract_mpi round robin ............. cotengra/core.py:4070
+#include <cuda.h>  // CUtensorMap (types only: the encoder is fetched through cudaGetDriverEntryPoint)
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <atomic>
@@ -228,6 +230,97 @@ int launch_dmmastream(const int64_t* h, const int64_t* d, const void* A, const v
   return CTGB_OK;
 }
 
+std::atomic<int64_t> g_tmap_launches{0};
+
+// Tensor map for the A tile of the tcgen05 kernel.  The tile is described in A's memory order by
+// the descriptor's load list (ext, stride), smallest stride first; adjacent entries that continue
+// each other coalesce into box dims.  If at most four box dims remain, the innermost is contiguous
+// and everything is 16-byte granular, ONE cp.async.bulk.tensor fetches the tile: dims 0..n-1 are
+// the box (coordinates 0), and one more dim of stride 16 bytes carries the tile's base offset as
+// its coordinate (tensor-map strides need not nest).  Returns the rank (2..5) or 0.
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+int tc05_make_tensor_map(const int64_t* h, const void* A, CUtensorMap* tm) {
+  static EncodeTiledFn encode = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      encode = (EncodeTiledFn)fn;
+    else
+      cudaGetLastError();
+  }
+  if (!encode || ((uintptr_t)A & 15u)) return 0;
+  struct Dim { uint64_t ext, stride; } box[8];
+  int nb = 0;
+  const int n_lda = (int)h[W_NLDA];
+  for (int i = 0; i < n_lda; ++i) {
+    const uint64_t ext = (uint64_t)h[OFF_LDA + 4 * i], st = (uint64_t)h[OFF_LDA + 4 * i + 1];
+    if (h[OFF_LDA + 4 * i + 1] <= 0) return 0;
+    if (nb && st == box[nb - 1].stride * box[nb - 1].ext) {
+      box[nb - 1].ext *= ext;
+    } else {
+      if (nb == 4) return 0;
+      box[nb].ext = ext;
+      box[nb].stride = st;
+      ++nb;
+    }
+  }
+  // a box dim holds at most 256 elements: split longer (contiguous) ones
+  for (int i = 0; i < nb; ++i) {
+    while (box[i].ext > 256) {
+      uint64_t f = 256;
+      while (f > 1 && box[i].ext % f) --f;
+      if (f < 2 || nb == 4) return 0;
+      for (int j = nb; j > i + 1; --j) box[j] = box[j - 1];
+      box[i + 1].ext = box[i].ext / f;
+      box[i + 1].stride = box[i].stride * f;
+      box[i].ext = f;
+      ++nb;
+    }
+  }
+  if (nb == 0 || box[0].stride != 1 || (box[0].ext & 1)) return 0;
+  uint64_t prod = 1;
+  for (int i = 0; i < nb; ++i) {
+    if (box[i].ext > 256 || (i && (box[i].stride & 1))) return 0;
+    prod *= box[i].ext;
+  }
+  if (prod != 128 * 16) return 0;
+  // base offsets of the tiles: sums of grid-dim digits times even strides, below 2^32 elements
+  uint64_t reach = 0;
+  auto grid = [&](int off, int n, int width, int col) -> bool {
+    for (int i = 0; i < n; ++i) {
+      const int64_t e = h[off + i * width], st = h[off + i * width + col];
+      if (st < 0 || (st & 1)) return false;
+      reach += (uint64_t)(e - 1) * (uint64_t)st;
+    }
+    return true;
+  };
+  if (!grid(OFF_GM, (int)h[W_NGM], 4, 2) || !grid(OFF_GK, (int)h[W_NGK], 4, 2) || !grid(OFF_GB, (int)h[W_NGB], 5, 2))
+    return 0;
+  if (reach >= (1ull << 32)) return 0;
+  cuuint64_t gdim[5], gstr[4];
+  cuuint32_t bdim[5], estr[5];
+  for (int i = 0; i < nb; ++i) {
+    gdim[i] = box[i].ext;
+    bdim[i] = (cuuint32_t)box[i].ext;
+    estr[i] = 1;
+    if (i) gstr[i - 1] = box[i].stride * 8;
+  }
+  gdim[nb] = 1ull << 31;  // offset dim: coordinate = base offset in 16-byte units
+  bdim[nb] = 1;
+  estr[nb] = 1;
+  gstr[nb - 1] = 16;
+  const CUresult rc = encode(tm, CU_TENSOR_MAP_DATA_TYPE_UINT64, (cuuint32_t)(nb + 1), const_cast<void*>(A), gdim, gstr,
+                             bdim, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                             CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return rc == CUDA_SUCCESS ? nb + 1 : 0;
+}
+
 // complex64 on tcgen05: prepare B' (hi/lo, tile order) once, then the warp-specialised kernel
 template <int NT>
 int launch_tc05(const int64_t* h, const int64_t* d, const void* A, const void* B, void* C, cudaStream_t st) {
@@ -291,8 +384,14 @@ int launch_tc05(const int64_t* h, const int64_t* d, const void* A, const void* B
     }
     CUDA_TRY(cudaMemsetAsync(C, 0, (size_t)h[W_CELEMS] * sizeof(float2), st));
   }
+  CUtensorMap tm;
+  memset(&tm, 0, sizeof(tm));
+  // (CTGB_NO_TENSOR_MAP=1 is a measurement knob: bulk-copy / gather staging only)
+  static const bool tm_off = getenv("CTGB_NO_TENSOR_MAP") != nullptr;
+  const int tm_rank = tm_off ? 0 : tc05_make_tensor_map(h, A, &tm);
+  if (tm_rank) g_tmap_launches.fetch_add(1, std::memory_order_relaxed);
   tc05_kernel<NT><<<(unsigned)grid, Cfg::THREADS, smem, st>>>(d, (const float2*)A, Bp, (float2*)C, (unsigned)sa,
-                                                               (unsigned)nb, b_stat);
+                                                               (unsigned)nb, b_stat, tm, tm_rank);
   g_launches.fetch_add(1, std::memory_order_relaxed);
   cudaError_t e = cudaGetLastError();
   cudaFreeAsync(Bp, st);
@@ -500,6 +599,7 @@ int ctgb_desc_words(void) { return DESC_WORDS; }
 int ctgb_single_desc_words(void) { return SDESC_WORDS; }
 const char* ctgb_last_error(void) { return g_err.c_str(); }
 int64_t ctgb_launch_count(void) { return g_launches.load(); }
+int64_t ctgb_tensor_map_launches(void) { return g_tmap_launches.load(); }
 
 int ctgb_device_info(int* sm_count, int* cc_major, int* cc_minor, size_t* smem_optin_bytes) {
   DevInfo& d = devinfo();

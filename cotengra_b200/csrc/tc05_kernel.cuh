@@ -8,7 +8,9 @@
 // mbarriers:
 //
 //   warps  8-11  A producers   the A tile of a k-step is fetched in A's MEMORY order
-//                              into a staging ring (SA deep, 16 KB each): TMA bulk copies
+//                              into a staging ring (SA deep, 16 KB each): ONE tensor-map TMA
+//                              copy (cp.async.bulk.tensor, a <= 4-D box of A's coalesced dims +
+//                              an offset dim) when the tile is such a box; else TMA bulk copies
 //                              of whole contiguous runs (cp.async.bulk + complete_tx) when
 //                              the tile is made of runs >= 128 B, an 8-byte cp.async
 //                              gather otherwise.  The ring only holds raw data, so it is
@@ -81,7 +83,8 @@ struct RingPos {
 template <int NT>
 __global__ void __launch_bounds__(448, 1)
 tc05_kernel(const int64_t* __restrict__ D, const float2* __restrict__ A, const float* __restrict__ Bp,
-            float2* __restrict__ C, const unsigned SA, const unsigned NB, const int b_stat) {
+            float2* __restrict__ C, const unsigned SA, const unsigned NB, const int b_stat,
+            const __grid_constant__ CUtensorMap tmA, const int tm_rank) {
   using Cfg = Tc05Cfg<NT>;
   constexpr int MT = Cfg::MT, TI = Cfg::TI, A_TILE = Cfg::A_TILE;
   constexpr int GROUP = 128;  // threads of the scatter group / of the A producers
@@ -287,7 +290,28 @@ tc05_kernel(const int64_t* __restrict__ D, const float2* __restrict__ A, const f
         const float2* src = A + tA + kbA[step];
         float2* dst = stg + (size_t)sa * A_TILE;
         const unsigned bar = (unsigned)__cvta_generic_to_shared(&stg_full[sa]);
-        if (bulk_a) {
+        if (tm_rank) {
+          // ONE tensor-map TMA copy per k-step (cp.async.bulk.tensor, SASS UTMALDG): the tile is a
+          // box of up to four coalesced dims of A in memory order, its position the coordinate of a
+          // fifth "offset" dim of stride 16 bytes (tc05_make_tensor_map)
+          const unsigned bytes = ptid == 0 ? (unsigned)A_TILE * 8u : 0u;
+          asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.expect_tx.shared::cta.b64 st, [%0], %1;\n\t}\n" ::"r"(bar),
+                       "r"(bytes)
+                       : "memory");
+          if (ptid == 0) {
+            const unsigned d = (unsigned)__cvta_generic_to_shared(dst);
+            const unsigned long long tm = reinterpret_cast<unsigned long long>(&tmA);
+            const int c = (int)((unsigned long long)(tA + kbA[step]) >> 1);  // 16-byte units
+            if (tm_rank == 2)
+              asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];\n" ::"r"(d), "l"(tm), "r"(0), "r"(c), "r"(bar) : "memory");
+            else if (tm_rank == 3)
+              asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];\n" ::"r"(d), "l"(tm), "r"(0), "r"(0), "r"(c), "r"(bar) : "memory");
+            else if (tm_rank == 4)
+              asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5}], [%6];\n" ::"r"(d), "l"(tm), "r"(0), "r"(0), "r"(0), "r"(c), "r"(bar) : "memory");
+            else
+              asm volatile("cp.async.bulk.tensor.5d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5, %6}], [%7];\n" ::"r"(d), "l"(tm), "r"(0), "r"(0), "r"(0), "r"(0), "r"(c), "r"(bar) : "memory");
+          }
+        } else if (bulk_a) {
           const bool mine = (unsigned)ptid < nruns;
           const unsigned bytes = mine ? run_a * 8u : 0u;
           asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.expect_tx.shared::cta.b64 st, [%0], %1;\n\t}\n" ::"r"(bar),

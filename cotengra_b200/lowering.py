@@ -63,6 +63,8 @@ VAR_DMMA3M_128x32, VAR_DMMA3M_256x16, VAR_DMMASTREAM, VAR_DOTSTREAM, VAR_DOTSTRE
 VAR_DMMA_32x32 = 18
 DMMASTREAM_MAX_N = 16  # the kernel takes N <= 32, but at N = 32 the staged 256x32 policy is faster (31.8 vs 26 TFLOP/s)
 TC05_VARIANTS = (VAR_TC05_128x64, VAR_TC05_128x32, VAR_TC05_128x16)
+TC05_MAX_K = 2048        # 128 k-steps (the kernel's k table); beyond 256 as split-K chunks of 256
+TC05_CHUNK_STEPS = 16    # k-steps (of 16) accumulated in TMEM before a round-to-nearest fold
 # (MT, NT, KT) of every kernel variant -- must match ctg_b200.cu's dispatch
 VARIANT_TILES = {
     VAR_SIMT_64x64: (64, 64, 8),
@@ -351,8 +353,11 @@ def choose_variant(dtype, B, M, N, K, allow_dmma=True, allow_stream=True, allow_
     if N <= 8 and M >= 64:
         return VAR_ROW_256x4 if N <= 4 else VAR_ROW_128x8
     # complex64 dense nodes with exact power-of-two tiles: tcgen05 (kind::tf32 x3, TMEM)
+    # (K > 256 runs as split-K over chunks of 256: every chunk accumulates in TMEM from zero and
+    # the chunks meet in fp32 atomics, i.e. round-to-nearest adds -- the tensor core's own
+    # accumulation truncates, which is why a single TMEM accumulation stops at K = 256)
     if (allow_dmma and allow_tc05 and dtype == "complex64" and M % 128 == 0 and K % 16 == 0
-            and K <= 256 and M * N * K >= 1 << 20):
+            and K <= TC05_MAX_K and M * N * K >= 1 << 20):
         if N % 64 == 0:
             return VAR_TC05_128x64
         if N % 32 == 0:
@@ -467,6 +472,8 @@ def build_pair_desc(dims: PairDims, dtype, accumulate=False, sm_count=148,
             splitk = min(steps_k, 4 * sm_count)
         if variant == VAR_DMMA_32x32 and tiles == 1:
             splitk = min(steps_k, 2 * sm_count)  # two resident CTAs per SM
+        if variant in TC05_VARIANTS and steps_k > TC05_CHUNK_STEPS:
+            splitk = max(splitk, -(-steps_k // TC05_CHUNK_STEPS))  # K > 256: chunks of 256 (accuracy)
     if splitk > 1:
         per = -(-steps_k // splitk)
         splitk = -(-steps_k // per)

@@ -170,6 +170,57 @@ def test_dotstream4_ragged_k_falls_back():
     assert rel_err(got, a @ b) < 1e-10
 
 
+# ------------------------------------------------------------------ tensor-map TMA staging (tcgen05 kernel)
+@pytest.mark.parametrize("layout", ["rows_contiguous", "k_inner", "five_dims", "short_runs"])
+def test_tc05_tensor_map_staging(layout):
+    """complex64 dense nodes whose A tile is a box of <= 4 coalesced dims: the staging ring is fed by
+    ONE cp.async.bulk.tensor per k-step (SASS UTMALDG); same results as numpy, and the launch counter
+    shows the path was taken."""
+    from cotengra_b200 import _lib
+
+    rng = np.random.default_rng(4)
+
+    def mk(shape):
+        return (rng.uniform(-1, 1, size=shape) + 1j * rng.uniform(-1, 1, size=shape)).astype(np.complex64)
+
+    if layout == "rows_contiguous":      # A[k, m]: m contiguous -> box (128 m) x (16 k)
+        eq, sa, sb = "km,kn->mn", (64, 4096), (64, 64)
+    elif layout == "k_inner":            # A[m, k]: k contiguous
+        eq, sa, sb = "mk,kn->mn", (4096, 64), (64, 64)
+    elif layout == "five_dims":          # interleaved binary dims, as on a Sycamore stem
+        eq, sa, sb = "abcdefgh,cfhn->abdegn", (8, 8, 4, 8, 4, 4, 8, 4), (4, 4, 4, 32)
+    else:                                # runs of 4 elements (32 B): too short for bulk copies
+        eq, sa, sb = "makb,kbn->man", (64, 4, 16, 4), (16, 4, 64)   # m, a kept; k, b contracted
+    a, b = mk(sa), mk(sb)
+    before = _lib.tensor_map_launches()
+    got = cb.einsum(eq, a, b)
+    used = _lib.tensor_map_launches() - before
+    want = np.einsum(eq, a.astype(np.complex128), b.astype(np.complex128))
+    assert rel_err(got, want) < 1e-5
+    _note(f"tensor_map_used:{layout}", int(used))
+    if layout in ("rows_contiguous", "k_inner"):
+        assert used == 1
+
+
+@pytest.mark.parametrize("shape", [(4096, 128, 1024), (2048, 64, 2048), (8192, 32, 512), (1024, 256, 272)])
+def test_tc05_long_k_as_split_k_chunks(shape):
+    """complex64 dense nodes with K > 256 (the m12 slice has M = 2^17, N = 2^11, K = 2^10): chunks of
+    256 accumulate in TMEM and meet in fp32 atomics, so the truncating tensor-core accumulation never
+    runs longer than before; 1e-5 against complex128."""
+    M, N, K = shape
+    rng = np.random.default_rng(K)
+    a = (rng.uniform(-1, 1, (M, K)) + 1j * rng.uniform(-1, 1, (M, K))).astype(np.complex64)
+    b = (rng.uniform(-1, 1, (K, N)) + 1j * rng.uniform(-1, 1, (K, N))).astype(np.complex64)
+    dims = L.classify_pair("mk", a.shape, "kn", b.shape, "mn")
+    plan = L.build_pair_desc(dims, "complex64", c_dense_elems=M * N)
+    assert plan.variant in L.TC05_VARIANTS
+    steps = int(plan.words[L.W_STEPS_K])
+    assert -(-steps // plan.splitk) <= L.TC05_CHUNK_STEPS
+    got = cb.einsum("mk,kn->mn", a, b)
+    want = a.astype(np.complex128) @ b.astype(np.complex128)
+    assert rel_err(got, want) < 1e-5
+
+
 # ------------------------------------------------------------------ check_zero
 @pytest.mark.parametrize("name,which", [("lattice6x6_d3_sliced", 0), ("rand_r3_o0_hi0_ho1_root_s666_sliced", 1),
                                         ("lattice4x4_sliced", 1)])
