@@ -170,6 +170,44 @@ int launch_rowstream(const int64_t* h, const int64_t* d, const void* A, const vo
 }
 
 template <typename T>
+int launch_rowstream_longk(const int64_t* h, const int64_t* d, const void* A, const void* B, void* C, cudaStream_t st) {
+  DevInfo& di = devinfo();
+  if (!di.ok) return fail(CTGB_E_CUDA, "no CUDA device");
+  if constexpr (sizeof(T) > 8) {
+    return fail(CTGB_E_VALUE, "the long-k row stream takes 8-byte and narrower element types");
+  } else {
+    const int N = (int)h[W_NTA], K = (int)h[W_KTA];
+    if (N > RSK_NMAX || K > RSK_KMAX || h[W_TILES_N] != 1 || h[W_TILES_B] != 1 || h[W_STEPS_K] != 1 ||
+        h[W_SPLITK] != 1 || h[W_PGM] >= 0 && (h[W_MFULL] % h[W_MTEXT]) != 0 || h[W_PGN] >= 0 || h[W_PGK] >= 0)
+      return fail(CTGB_E_VALUE, "descriptor does not fit the long-k row-stream kernel");
+    // offset(k) must decompose as chunk_base[k / 8] + in_chunk[k % 8]
+    auto koff = [&](long long e) {
+      long long o = 0;
+      for (int i = 0; i < (int)h[W_NTK]; ++i) {
+        o += (e % h[OFF_TK + 3 * i]) * h[OFF_TK + 3 * i + 1];
+        e /= h[OFF_TK + 3 * i];
+      }
+      return o;
+    };
+    for (long long e = 0; e < K; ++e)
+      if (koff(e) != koff(e - e % 8) + koff(e % 8)) return fail(CTGB_E_VALUE, "k offsets do not split into chunks of 8");
+    const unsigned long long M = (unsigned long long)h[W_MTA] * (unsigned long long)h[W_TILES_M];
+    if (M >= (1ull << 32)) return fail(CTGB_E_VALUE, "too many rows for the row-stream kernel");
+    unsigned long long blocks = (M + 511) / 512;
+    const unsigned long long cap = (unsigned long long)di.sms * 6;
+    if (blocks > cap) blocks = cap;
+    if (blocks == 0) return CTGB_OK;
+    if (h[W_SCALE_A] != 0 || h[W_FACTOR_C] != 0)
+      rowstream_longk_kernel<T, true><<<(unsigned)blocks, 256, 0, st>>>(d, (const T*)A, (const T*)B, (T*)C);
+    else
+      rowstream_longk_kernel<T><<<(unsigned)blocks, 256, 0, st>>>(d, (const T*)A, (const T*)B, (T*)C);
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    CUDA_TRY(cudaGetLastError());
+    return CTGB_OK;
+  }
+}
+
+template <typename T>
 int launch_dotstream(const int64_t* h, const int64_t* d, const void* A, const void* B, void* C, cudaStream_t st) {
   DevInfo& di = devinfo();
   if (!di.ok) return fail(CTGB_E_CUDA, "no CUDA device");
@@ -403,6 +441,7 @@ template <typename T>
 int launch_gett_typed(const int64_t* h, const int64_t* d, const void* A, const void* B, void* C, cudaStream_t st) {
   const int variant = (int)h[W_VARIANT];
   if (variant == VAR_ROWSTREAM) return launch_rowstream<T>(h, d, A, B, C, st);
+  if (variant == VAR_ROWSTREAM_K) return launch_rowstream_longk<T>(h, d, A, B, C, st);
   if (variant == VAR_DMMASTREAM) return launch_dmmastream(h, d, A, B, C, st);
   if (variant == VAR_DOTSTREAM || variant == VAR_DOTSTREAM4) return launch_dotstream<T>(h, d, A, B, C, st);
   if constexpr (std::is_same<T, float2>::value) {
@@ -724,8 +763,11 @@ int ctgb_plan_create(const ctgb_plan_desc* pd, ctgb_plan** out) {
     if (pd->strip_exponent && n.kind == 0) {
       const int64_t* w = n.desc;
       q.measure_after = w[W_SPLITK] > 1 || w[W_VARIANT] == VAR_DOTSTREAM || w[W_VARIANT] == VAR_DOTSTREAM4;
-      // (the block-reduction epilogue of KRED runs once: its result is measured afterwards as well)
+      // (the block-reduction epilogue of KRED runs once: its result is measured afterwards as well;
+      // so is a tcgen05 node whose contracted range is folded into C chunk by chunk)
       q.measure_after |= w[W_VARIANT] == VAR_KRED;
+      q.measure_after |= (w[W_VARIANT] == VAR_TC05_128x64 || w[W_VARIANT] == VAR_TC05_128x32 ||
+                          w[W_VARIANT] == VAR_TC05_128x16) && w[W_STEPS_K] > TC05_CHUNK;
     }
     if (!n.invariant) per_slice += 1 + q.measure_after + (pd->strip_exponent && n.kind == 0 ? 1 : 0);
   }

@@ -84,6 +84,7 @@ enum : int {
   VAR_DOTSTREAM4 = 16,     // M, N <= 4 over a huge contracted range: a peeled stem tail times the other stem
   // (17: a DMMA-fragments-from-global variant of the next one, measured slower -- 11.1 vs 10.1 ms on
   //  the M = N = 32, K = 2^25 node -- and removed)
+  VAR_ROWSTREAM_K = 19,    // N <= 8, 8 < K <= 64, 8-byte and narrower types: the row stream in chunks of 8 k
   VAR_DMMA_32x32 = 18      // fp64 DMMA, one 32 x 32 tile with split-K over all SMs, two CTAs per SM: a few
                            // peeled stem tails times the other stem (M, N <= 32 over K ~ 2^25)
 };

@@ -221,3 +221,174 @@ rowstream_kernel(const int64_t* __restrict__ D, const T* __restrict__ A, const T
   }
   if constexpr (STRIP) strip_end(sctx);
 }
+
+// ---- skinny nodes whose contracted space is too long for the kernel above (N <= 8, 8 < K <= 64;
+// 8-byte and narrower element types -- complex128 takes the DMMA stream kernel): the same
+// thread-per-row stream with the k range walked in chunks of 8.  The m12 slice has an
+// M = 2^26, N = 8, K = 64 complex64 node that the staged row policy ran at 0.32 of its roofline.
+// Two rows per thread; the offset of element k is chunk_base[k / 8] + in_chunk[k % 8] (the host
+// only picks this kernel when the k offsets decompose that way), B is broadcast from shared
+// memory, the 8 accumulators of a row stay in registers across the chunks.
+constexpr int RSK_KMAX = 64, RSK_NMAX = 8;
+
+template <typename T, bool STRIP = false>
+__global__ void __launch_bounds__(256, 3)
+rowstream_longk_kernel(const int64_t* __restrict__ D, const T* __restrict__ A, const T* __restrict__ B,
+                       T* __restrict__ C) {
+  __shared__ long long s_akoff[RSK_KMAX], s_bkoff[RSK_KMAX], s_bnoff[RSK_NMAX], s_cnoff[RSK_NMAX];
+  __shared__ long long s_msA[RS_MAXDIMS], s_msC[RS_MAXDIMS];
+  __shared__ unsigned s_mext[RS_MAXDIMS];
+  __shared__ T s_B[RSK_KMAX * RSK_NMAX];
+  const int tid = threadIdx.x;
+  const int n_tm = (int)D[W_NTM], n_gm = (int)D[W_NGM], n_tk = (int)D[W_NTK], n_tn = (int)D[W_NTN];
+  const int K = (int)D[W_KTA], N = (int)D[W_NTA];
+  const int n_m = n_tm + n_gm;
+  const bool accumulate = (D[W_FLAGS] & 1) != 0;
+  [[maybe_unused]] const bool quad8 = (D[W_FLAGS] & 16) != 0 && !accumulate && sizeof(T) == 8;
+  const bool pow2 = (D[W_FLAGS] & 8) != 0;
+  for (int d = tid; d < n_m; d += blockDim.x) {
+    if (d < n_tm) {
+      const int64_t* L = D + OFF_TM + d * 3;
+      s_mext[d] = (unsigned)L[0];
+      s_msA[d] = L[1];
+      s_msC[d] = L[2];
+    } else {
+      const int64_t* G = D + OFF_GM + (d - n_tm) * 4;
+      s_mext[d] = (unsigned)G[0];
+      s_msA[d] = G[2];
+      s_msC[d] = G[3];
+    }
+  }
+  if (tid < RSK_KMAX) {
+    long long a = 0, b = 0;
+    if (tid < K) {
+      unsigned e = tid;
+      for (int d = 0; d < n_tk; ++d) {
+        const int64_t* L = D + OFF_TK + d * 3;
+        const unsigned ext = (unsigned)L[0];
+        a += (long long)(e % ext) * L[1];
+        b += (long long)(e % ext) * L[2];
+        e /= ext;
+      }
+    }
+    s_akoff[tid] = a;
+    s_bkoff[tid] = b;
+  }
+  if (tid >= 64 && tid < 64 + RSK_NMAX) {
+    const int c = tid - 64;
+    long long b = 0, o = 0;
+    if (c < N) {
+      unsigned e = c;
+      for (int d = 0; d < n_tn; ++d) {
+        const int64_t* L = D + OFF_TN + d * 3;
+        const unsigned ext = (unsigned)L[0];
+        b += (long long)(e % ext) * L[1];
+        o += (long long)(e % ext) * L[2];
+        e /= ext;
+      }
+    }
+    s_bnoff[c] = b;
+    s_cnoff[c] = o;
+  }
+  __syncthreads();
+  for (int i = tid; i < RSK_KMAX * RSK_NMAX; i += blockDim.x) {
+    const int kk = i / RSK_NMAX, c = i % RSK_NMAX;
+    s_B[i] = (kk < K && c < N) ? B[s_bkoff[kk] + s_bnoff[c]] : zero_of<T>();
+  }
+  __syncthreads();
+  long long inoff[8];  // offsets inside a chunk of 8 k
+#pragma unroll
+  for (int kk = 0; kk < 8; ++kk) inoff[kk] = s_akoff[kk];
+  const int nchunks = (K + 7) >> 3;
+  [[maybe_unused]] StripCtx sctx;
+  if constexpr (STRIP) sctx = strip_begin(D);
+  const unsigned long long M = (unsigned long long)D[W_MTA] * (unsigned long long)D[W_TILES_M];
+  const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
+  constexpr int R = 2;
+  for (unsigned long long m0 = (unsigned long long)blockIdx.x * blockDim.x + tid; m0 < M; m0 += stride * R) {
+    long long oa[R], oc[R];
+    bool live[R];
+#pragma unroll
+    for (int i = 0; i < R; ++i) {
+      const unsigned long long m = m0 + (unsigned long long)i * stride;
+      live[i] = m < M;
+      unsigned e = live[i] ? (unsigned)m : 0u;
+      long long xa = 0, xc = 0;
+      for (int d = 0; d < n_m; ++d) {
+        const unsigned ext = s_mext[d];
+        const unsigned dig = pow2 ? (e & (ext - 1)) : (e % ext);
+        e = pow2 ? (e >> (31 - __clz(ext))) : (e / ext);
+        xa += (long long)dig * s_msA[d];
+        xc += (long long)dig * s_msC[d];
+      }
+      oa[i] = xa;
+      oc[i] = xc;
+    }
+    T acc[R][RSK_NMAX];
+#pragma unroll
+    for (int i = 0; i < R; ++i)
+#pragma unroll
+      for (int c = 0; c < RSK_NMAX; ++c) acc[i][c] = zero_of<T>();
+    for (int kc = 0; kc < nchunks; ++kc) {
+      const long long cb = s_akoff[kc * 8];  // chunk base (in_chunk[0] is 0)
+      T a[R][8];
+#pragma unroll
+      for (int i = 0; i < R; ++i)
+#pragma unroll
+        for (int kk = 0; kk < 8; ++kk) a[i][kk] = (kc * 8 + kk < K) ? A[oa[i] + cb + inoff[kk]] : zero_of<T>();
+#pragma unroll
+      for (int kk = 0; kk < 8; ++kk)
+#pragma unroll
+        for (int c = 0; c < RSK_NMAX; ++c) {
+          const T b = s_B[(kc * 8 + kk) * RSK_NMAX + c];
+#pragma unroll
+          for (int i = 0; i < R; ++i) mac(acc[i][c], a[i][kk], b);
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < R; ++i) {
+      if (!live[i]) continue;
+      if constexpr (STRIP) {
+        if (sctx.scale) {
+#pragma unroll
+          for (int c = 0; c < RSK_NMAX; ++c)
+            if (c < N) acc[i][c] = strip_apply(sctx, acc[i][c]);
+        } else {
+          int hmax = 0;
+#pragma unroll
+          for (int c = 0; c < RSK_NMAX; ++c)
+            if (c < N) hmax = max(hmax, strip_hi(acc[i][c]));
+          if (strip_hot<T>(sctx, hmax)) {
+#pragma unroll
+            for (int c = 0; c < RSK_NMAX; ++c)
+              if (c < N) strip_note(sctx, acc[i][c]);
+          }
+        }
+      }
+      T* pc = C + oc[i];
+      bool done = false;
+      if constexpr (sizeof(T) == 8) {
+        if (quad8) {
+#pragma unroll
+          for (int c = 0; c + 3 < RSK_NMAX; c += 4)
+            if (c < N) {
+              const unsigned long long* q = reinterpret_cast<const unsigned long long*>(&acc[i][c]);
+              asm volatile("st.global.v4.b64 [%0], {%1,%2,%3,%4};" ::"l"(pc + s_cnoff[c]), "l"(q[0]), "l"(q[1]), "l"(q[2]),
+                           "l"(q[3])
+                           : "memory");
+            }
+          done = true;
+        }
+      }
+      if (!done) {
+#pragma unroll
+        for (int c = 0; c < RSK_NMAX; ++c)
+          if (c < N) {
+            T* p = pc + s_cnoff[c];
+            *p = accumulate ? add_of(*p, acc[i][c]) : acc[i][c];
+          }
+      }
+    }
+  }
+  if constexpr (STRIP) strip_end(sctx);
+}

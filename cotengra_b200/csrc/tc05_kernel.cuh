@@ -59,6 +59,9 @@ struct Tc05Cfg {
   }
 };
 
+// k-steps (of 16) accumulated in TMEM before the epilogue folds them into C (K <= 256 per chunk)
+constexpr int TC05_CHUNK = 16;
+
 // one lane of a converged warp (the compiler keeps the surrounding code warp-uniform)
 __device__ __forceinline__ bool elect_one() {
   unsigned pred;
@@ -408,13 +411,18 @@ tc05_kernel(const int64_t* __restrict__ D, const float2* __restrict__ A, const f
         (1u << 4) | (2u << 7) | (2u << 10) | ((unsigned)((2 * NT) >> 3) << 17) | ((unsigned)(MT >> 4) << 24);
     const unsigned op_base = (unsigned)__cvta_generic_to_shared(op);
     const unsigned b_base = (unsigned)__cvta_generic_to_shared(sB);
-    unsigned g = 0;
+    unsigned g = 0, acq = 0;  // acq: accumulations started (TMEM buffer = acq & 1)
     RingPos rb;
     for (unsigned j = 0; j < nw; ++j) {
-      unsigned k0, k1;
-      work_krange(j, k0, k1);
-      const unsigned buf = j & 1;
-      mbar_wait(&tmem_empty[buf], ((j >> 1) & 1) ^ 1);  // epilogue of tile j-2 has drained this accumulator
+      unsigned kb, ke;
+      work_krange(j, kb, ke);
+      // a contracted range longer than TC05_CHUNK k-steps (K > 256) is accumulated chunk by chunk:
+      // every chunk starts a fresh TMEM accumulation, the epilogue folds it into C with
+      // round-to-nearest adds (the tensor core's own accumulation truncates)
+      for (unsigned k0 = kb; k0 < ke; k0 += TC05_CHUNK, ++acq) {
+      const unsigned k1 = min(ke, k0 + (unsigned)TC05_CHUNK);
+      const unsigned buf = acq & 1;
+      mbar_wait(&tmem_empty[buf], ((acq >> 1) & 1) ^ 1);  // the epilogue two accumulations back has drained it
       for (unsigned step = k0; step < k1; ++step, ++g, rb.next(NB)) {
         const unsigned ob = g & 1, sb = b_stat ? step : rb.idx;
         mbar_wait(&op_full[ob], (g >> 1) & 1);
@@ -462,6 +470,7 @@ tc05_kernel(const int64_t* __restrict__ D, const float2* __restrict__ A, const f
         }
         __syncwarp();
       }
+      }
     }
   } else if (warp < 8) {
     // ===================================================== EPILOGUE GROUP (warps 4-7)
@@ -471,9 +480,14 @@ tc05_kernel(const int64_t* __restrict__ D, const float2* __restrict__ A, const f
     const int r = quad * 32 + lane;
     const long long row_off = offMC[r];
     StripCtx sctx = strip_begin(D);  // fused strip_exponent
+    unsigned acq = 0;
     for (unsigned j = 0; j < nw; ++j) {
-      const unsigned buf = j & 1;
-      mbar_wait(&tmem_full[buf], (j >> 1) & 1);
+      unsigned kb, ke;
+      work_krange(j, kb, ke);
+      for (unsigned k0 = kb; k0 < ke; k0 += TC05_CHUNK, ++acq) {
+      const unsigned buf = acq & 1;
+      const bool rmw = k0 != kb;  // a later chunk of the same tile: add to what the first one stored
+      mbar_wait(&tmem_full[buf], (acq >> 1) & 1);
       asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
       float2* crow = C + ti_base[(j % TI) * 4 + 2] + row_off;
       // 32 fp32 columns (16 complex) per tcgen05.ld: one TMEM round trip per 128 bytes of a row
@@ -526,8 +540,22 @@ tc05_kernel(const int64_t* __restrict__ D, const float2* __restrict__ A, const f
           const int c0 = (col >> 1) + s4 * 4;
           const unsigned* w = v + s4 * 8;
           if (quad_ok) {
-            const unsigned long long q0 = ((unsigned long long)w[1] << 32) | w[0], q1 = ((unsigned long long)w[3] << 32) | w[2];
-            const unsigned long long q2 = ((unsigned long long)w[5] << 32) | w[4], q3 = ((unsigned long long)w[7] << 32) | w[6];
+            unsigned x[8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) x[e] = w[e];
+            if (rmw) {
+              // same thread, same addresses as the chunk before: program order makes the sum visible
+              unsigned long long p0, p1, p2, p3;
+              asm volatile("ld.global.v4.b64 {%0,%1,%2,%3}, [%4];\n" : "=l"(p0), "=l"(p1), "=l"(p2), "=l"(p3) : "l"(crow + offNC[c0]) : "memory");
+              const unsigned long long pp[4] = {p0, p1, p2, p3};
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                x[2 * e] = __float_as_uint(__uint_as_float(x[2 * e]) + __uint_as_float((unsigned)pp[e]));
+                x[2 * e + 1] = __float_as_uint(__uint_as_float(x[2 * e + 1]) + __uint_as_float((unsigned)(pp[e] >> 32)));
+              }
+            }
+            const unsigned long long q0 = ((unsigned long long)x[1] << 32) | x[0], q1 = ((unsigned long long)x[3] << 32) | x[2];
+            const unsigned long long q2 = ((unsigned long long)x[5] << 32) | x[4], q3 = ((unsigned long long)x[7] << 32) | x[6];
             asm volatile("st.global.v4.b64 [%0], {%1,%2,%3,%4};\n" ::"l"(crow + offNC[c0]), "l"(q0), "l"(q1), "l"(q2),
                          "l"(q3)
                          : "memory");
@@ -538,7 +566,7 @@ tc05_kernel(const int64_t* __restrict__ D, const float2* __restrict__ A, const f
               const float2 val = make_float2(__uint_as_float(w[2 * e]), __uint_as_float(w[2 * e + 1]));
               if (atomic) {
                 atomic_add_of(p, val);
-              } else if (accumulate) {
+              } else if (accumulate || rmw) {
                 *p = add_of(*p, val);
               } else {
                 *p = val;
@@ -550,6 +578,7 @@ tc05_kernel(const int64_t* __restrict__ D, const float2* __restrict__ A, const f
       asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
       __syncwarp();
       if (lane == 0) mbar_arrive(&tmem_empty[buf]);
+      }
     }
     strip_end(sctx);
   }

@@ -60,10 +60,10 @@ VAR_SIMT_64x64, VAR_KRED, VAR_DMMA_128x64, VAR_DMMA_64x128, VAR_DMMA_256x32 = 0,
 VAR_DMMA_256x16, VAR_ROW_128x8, VAR_ROW_256x4, VAR_ROWSTREAM = 5, 6, 7, 8
 VAR_TC05_128x64, VAR_TC05_128x32, VAR_TC05_128x16 = 9, 10, 11
 VAR_DMMA3M_128x32, VAR_DMMA3M_256x16, VAR_DMMASTREAM, VAR_DOTSTREAM, VAR_DOTSTREAM4 = 12, 13, 14, 15, 16
-VAR_DMMA_32x32 = 18
+VAR_DMMA_32x32, VAR_ROWSTREAM_K = 18, 19
 DMMASTREAM_MAX_N = 16  # the kernel takes N <= 32, but at N = 32 the staged 256x32 policy is faster (31.8 vs 26 TFLOP/s)
 TC05_VARIANTS = (VAR_TC05_128x64, VAR_TC05_128x32, VAR_TC05_128x16)
-TC05_MAX_K = 2048        # 128 k-steps (the kernel's k table); beyond 256 as split-K chunks of 256
+TC05_MAX_K = 2048        # 128 k-steps (the kernel's k table); beyond 256 in chunks of 256
 TC05_CHUNK_STEPS = 16    # k-steps (of 16) accumulated in TMEM before a round-to-nearest fold
 # (MT, NT, KT) of every kernel variant -- must match ctg_b200.cu's dispatch
 VARIANT_TILES = {
@@ -85,6 +85,7 @@ VARIANT_TILES = {
     VAR_DOTSTREAM: (1, 1, 2048),
     VAR_DOTSTREAM4: (4, 4, 1024),
     VAR_DMMA_32x32: (32, 32, 32),
+    VAR_ROWSTREAM_K: (256, 8, 64),
 }
 
 DTYPE_CODES = {"float32": 0, "float64": 1, "complex64": 2, "complex128": 3}
@@ -350,11 +351,15 @@ def choose_variant(dtype, B, M, N, K, allow_dmma=True, allow_stream=True, allow_
     if (allow_dmma and allow_stream and dtype == "complex128" and B == 1 and 4096 <= M < 1 << 32
             and ((N <= DMMASTREAM_MAX_N and K <= 32) or (N <= 8 and 8 < K <= 64))):
         return VAR_DMMASTREAM
+    # ... and the narrower element types: the row stream walked in chunks of 8 k
+    if (allow_stream and DTYPE_SIZES[dtype] <= 8 and N <= 8 and 8 < K <= 64 and B == 1
+            and 4096 <= M < 1 << 32):
+        return VAR_ROWSTREAM_K
     if N <= 8 and M >= 64:
         return VAR_ROW_256x4 if N <= 4 else VAR_ROW_128x8
     # complex64 dense nodes with exact power-of-two tiles: tcgen05 (kind::tf32 x3, TMEM)
-    # (K > 256 runs as split-K over chunks of 256: every chunk accumulates in TMEM from zero and
-    # the chunks meet in fp32 atomics, i.e. round-to-nearest adds -- the tensor core's own
+    # (K > 256 runs in chunks of 256 inside the kernel: every chunk accumulates in TMEM from zero
+    # and the epilogue folds it into C with round-to-nearest adds -- the tensor core's own
     # accumulation truncates, which is why a single TMEM accumulation stops at K = 256)
     if (allow_dmma and allow_tc05 and dtype == "complex64" and M % 128 == 0 and K % 16 == 0
             and K <= TC05_MAX_K and M * N * K >= 1 << 20):
@@ -472,8 +477,6 @@ def build_pair_desc(dims: PairDims, dtype, accumulate=False, sm_count=148,
             splitk = min(steps_k, 4 * sm_count)
         if variant == VAR_DMMA_32x32 and tiles == 1:
             splitk = min(steps_k, 2 * sm_count)  # two resident CTAs per SM
-        if variant in TC05_VARIANTS and steps_k > TC05_CHUNK_STEPS:
-            splitk = max(splitk, -(-steps_k // TC05_CHUNK_STEPS))  # K > 256: chunks of 256 (accuracy)
     if splitk > 1:
         per = -(-steps_k // splitk)
         splitk = -(-steps_k // per)
@@ -535,6 +538,21 @@ def build_pair_desc(dims: PairDims, dtype, accumulate=False, sm_count=148,
     if variant == VAR_DMMASTREAM and (pn is not None or pk is not None or (pm is not None and pm[1] % pm[2] != 0)):
         return build_pair_desc(dims, dtype, accumulate=accumulate, sm_count=sm_count, variant=VAR_DMMA_256x16,
                                allow_dmma=allow_dmma, c_dense_elems=c_dense_elems, force_splitk=force_splitk)
+    if variant == VAR_ROWSTREAM_K:
+        # exact tiles, and the k offsets must decompose as chunk_base[k // 8] + in_chunk[k % 8]
+        def _koff(e, col):
+            o = 0
+            for d in tk:
+                o += (e % d[0]) * d[col]
+                e //= d[0]
+            return o
+        ok8 = all(_koff(e, 1) == _koff(e - e % 8, 1) + _koff(e % 8, 1) for e in range(KTa))
+        if (not ok8 or pn is not None or pk is not None or (pm is not None and pm[1] % pm[2] != 0)
+                or DTYPE_SIZES[dtype] > 8 or not (N <= 8 and K <= 64 and B == 1 and M < 1 << 32)):
+            return build_pair_desc(dims, dtype, accumulate=accumulate, sm_count=sm_count,
+                                   variant=VAR_ROW_256x4 if N <= 4 else VAR_ROW_128x8,
+                                   allow_dmma=allow_dmma, c_dense_elems=c_dense_elems,
+                                   force_splitk=force_splitk)
     if variant == VAR_ROWSTREAM and pm is not None and pm[1] % pm[2] != 0:
         # ragged blocked m dim: fall back to the staged row policy
         return build_pair_desc(dims, dtype, accumulate=accumulate, sm_count=sm_count,

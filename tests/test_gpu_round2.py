@@ -162,6 +162,36 @@ def test_dmmastream_long_k_skinny(shape):
     assert rel_err(got, a @ b) < 1e-10
 
 
+@pytest.mark.parametrize("dtype", ["complex64", "float32", "float64"])
+@pytest.mark.parametrize("shape", [((1 << 16, 64), (64, 8)), ((1 << 14, 48), (48, 5)), ((1 << 15, 24), (24, 8)),
+                                   ((1 << 14, 6, 6), (6, 6, 7)), ((12288, 40), (40, 3))])
+def test_rowstream_long_k(dtype, shape):
+    """8-byte and narrower element types, N <= 8, 8 < K <= 64: the row stream walked in chunks of 8 k
+    (the m12 slice's M = 2^26, N = 8, K = 64 complex64 node)."""
+    sa, sb = shape
+    a, b = make_arrays([sa, sb], "complex128", seed=sum(sa))
+    if np.dtype(dtype).kind != "c":
+        a, b = a.real, b.real
+    a, b = a.astype(dtype), b.astype(dtype)
+    ta = "m" + "kl"[: len(sa) - 1]
+    tb = "kl"[: len(sb) - 1] + "n"
+    dims = L.classify_pair(ta, sa, tb, sb, "mn")
+    plan = L.build_pair_desc(dims, dtype, c_dense_elems=sa[0] * sb[-1])
+    assert plan.variant == L.VAR_ROWSTREAM_K, plan.variant
+    got = cb.einsum(f"{ta},{tb}->mn", a, b)
+    wide = np.complex128 if np.dtype(dtype).kind == "c" else np.float64
+    want = np.einsum(f"{ta},{tb}->mn", a.astype(wide), b.astype(wide))
+    assert rel_err(got, want) < (1e-10 if dtype == "float64" else 1e-5)
+    # inside a tree with stripped exponents (the STRIP instantiation: scan for max|C|, lazy scaling)
+    c = make_arrays([(sb[-1], 4)], "complex128", seed=3)[0]
+    c = (c.real if np.dtype(dtype).kind != "c" else c).astype(dtype)
+    spec = cb.TreeSpec([tuple(ta), tuple(tb), ("n", "z")], ("m", "z"),
+                       {**{ix: d for ix, d in zip(ta, sa)}, **{ix: d for ix, d in zip(tb, sb)}, "z": 4}, [(0, 1), (3, 2)])
+    m, e = cb.contract_tree(spec, [a, b, c], strip_exponent=True)
+    want2 = want @ c.astype(wide)
+    assert rel_err(np.asarray(m).astype(wide) * 10.0**e, want2) < (1e-10 if dtype == "float64" else 2e-5)
+
+
 def test_dotstream4_ragged_k_falls_back():
     a, b = make_arrays([(3, 1000003), (1000003, 4)], "complex128", seed=5)
     dims = L.classify_pair("mk", a.shape, "kn", b.shape, "mn")
@@ -203,10 +233,10 @@ def test_tc05_tensor_map_staging(layout):
 
 
 @pytest.mark.parametrize("shape", [(4096, 128, 1024), (2048, 64, 2048), (8192, 32, 512), (1024, 256, 272)])
-def test_tc05_long_k_as_split_k_chunks(shape):
+def test_tc05_long_k_in_chunks(shape):
     """complex64 dense nodes with K > 256 (the m12 slice has M = 2^17, N = 2^11, K = 2^10): chunks of
-    256 accumulate in TMEM and meet in fp32 atomics, so the truncating tensor-core accumulation never
-    runs longer than before; 1e-5 against complex128."""
+    256 accumulate in TMEM and are folded into C by the epilogue with round-to-nearest adds, so the
+    truncating tensor-core accumulation never runs longer than before; 1e-5 against complex128."""
     M, N, K = shape
     rng = np.random.default_rng(K)
     a = (rng.uniform(-1, 1, (M, K)) + 1j * rng.uniform(-1, 1, (M, K))).astype(np.complex64)
@@ -214,8 +244,6 @@ def test_tc05_long_k_as_split_k_chunks(shape):
     dims = L.classify_pair("mk", a.shape, "kn", b.shape, "mn")
     plan = L.build_pair_desc(dims, "complex64", c_dense_elems=M * N)
     assert plan.variant in L.TC05_VARIANTS
-    steps = int(plan.words[L.W_STEPS_K])
-    assert -(-steps // plan.splitk) <= L.TC05_CHUNK_STEPS
     got = cb.einsum("mk,kn->mn", a, b)
     want = a.astype(np.complex128) @ b.astype(np.complex128)
     assert rel_err(got, want) < 1e-5
