@@ -503,7 +503,12 @@ int launch_single_typed(const int64_t* h, const int64_t* d, const void* X, void*
   if (n <= 0) return CTGB_OK;
   long long blocks = (n + 255) / 256;
   if (blocks > 148 * 16) blocks = 148 * 16;
-  single_kernel<T><<<(unsigned)blocks, 256, 0, st>>>(d, (const T*)X, (T*)out);
+  if (h[S_SUM_ELEMS] >= 1024 && n <= 148 * 16) {
+    // few outputs over a long summed range: one block per output element
+    single_reduce_kernel<T><<<(unsigned)n, 256, 0, st>>>(d, (const T*)X, (T*)out);
+  } else {
+    single_kernel<T><<<(unsigned)blocks, 256, 0, st>>>(d, (const T*)X, (T*)out);
+  }
   g_launches.fetch_add(1, std::memory_order_relaxed);
   CUDA_TRY(cudaGetLastError());
   return CTGB_OK;

@@ -659,6 +659,48 @@ __global__ void single_kernel(const int64_t* __restrict__ D, const T* __restrict
   }
 }
 
+// the same with a block per output element: few outputs, a long summed range (a full trace or a
+// reduction of a large preprocessing operand) -- the thread-per-output kernel above would walk the
+// summed range serially
+template <typename T>
+__global__ void __launch_bounds__(256) single_reduce_kernel(const int64_t* __restrict__ D, const T* __restrict__ X,
+                                                            T* __restrict__ out) {
+  __shared__ T s_part[8];
+  const int n_o = (int)D[S_NO], n_s = (int)D[S_NS];
+  const long long out_elems = D[S_OUT_ELEMS], sum_elems = D[S_SUM_ELEMS];
+  const bool accumulate = (D[S_FLAGS] & 1) != 0;
+  for (long long o = blockIdx.x; o < out_elems; o += gridDim.x) {
+    long long e = o, xo = 0, oo = 0;
+    for (int d = 0; d < n_o; ++d) {
+      const int64_t* L = D + OFF_SO + d * 3;
+      const long long dig = e % L[0];
+      e /= L[0];
+      xo += dig * L[1];
+      oo += dig * L[2];
+    }
+    T acc = zero_of<T>();
+    for (long long s = threadIdx.x; s < sum_elems; s += blockDim.x) {
+      long long e2 = s, xs = 0;
+      for (int d = 0; d < n_s; ++d) {
+        const int64_t* L = D + OFF_SS + d * 2;
+        xs += (e2 % L[0]) * L[1];
+        e2 /= L[0];
+      }
+      acc = add_of(acc, X[xo + xs]);
+    }
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) acc = add_of(acc, shfl_down_of(acc, d));
+    if ((threadIdx.x & 31) == 0) s_part[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      T v = s_part[0];
+      for (int w = 1; w < 8; ++w) v = add_of(v, s_part[w]);
+      out[oo] = accumulate ? add_of(out[oo], v) : v;
+    }
+    __syncthreads();
+  }
+}
+
 // ------------------------------------------------------------------ strip_exponent helpers
 // contract.py:816-829: factor = max|p|; exponent += log10(factor); p /= factor  (fused into the
 // kernels' epilogues, StripCtx above; absmax_kernel serves the nodes that add partial sums atomically)

@@ -249,6 +249,16 @@ def test_tc05_long_k_in_chunks(shape):
     assert rel_err(got, want) < 1e-5
 
 
+@pytest.mark.parametrize("eq,shape", [("abcd->", (64, 32, 64, 16)), ("abca->b", (96, 8, 500, 96)), ("ab->a", (7, 200000)),
+                                      ("aabc->c", (300, 300, 40, 3))])
+def test_single_operand_long_reductions(eq, shape):
+    """few outputs over a long summed range run one block per output element."""
+    (x,) = make_arrays([shape], "complex128", seed=len(eq))
+    got = cb.einsum(eq, x)
+    want = np.einsum(eq, x)
+    assert rel_err(got, want) < 1e-10
+
+
 # ------------------------------------------------------------------ check_zero
 @pytest.mark.parametrize("name,which", [("lattice6x6_d3_sliced", 0), ("rand_r3_o0_hi0_ho1_root_s666_sliced", 1),
                                         ("lattice4x4_sliced", 1)])
