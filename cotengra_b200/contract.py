@@ -191,7 +191,10 @@ class TreeExecutor:
         if fuse and contractions is None:
             from .fusion import fuse_stems
 
-            self.exec_spec, self.fusion = fuse_stems(self.spec, dtype_name(dtype))
+            # (``fuse`` may be a dict of planner options -- min_big, ratio, min_gain, model -- e.g. to
+            # force fusion on small trees in tests)
+            opts = fuse if isinstance(fuse, dict) else {}
+            self.exec_spec, self.fusion = fuse_stems(self.spec, dtype_name(dtype), **opts)
         ir = self.exec_spec.contractions() if contractions is None else contractions
         torch = _torch()
         self.device = torch.device("cuda", torch.cuda.current_device() if device is None else device)

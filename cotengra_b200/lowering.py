@@ -84,7 +84,7 @@ VARIANT_TILES = {
     VAR_DMMASTREAM: (256, 32, 64),
     VAR_DOTSTREAM: (1, 1, 2048),
     VAR_DOTSTREAM4: (4, 4, 1024),
-    VAR_DMMA_32x32: (32, 32, 32),
+    VAR_DMMA_32x32: (32, 32, 16),
     VAR_ROWSTREAM_K: (256, 8, 64),
 }
 

@@ -97,6 +97,27 @@ def test_fused_vs_unfused_large_slice_c64():
     assert max(errs.values()) < 3e-3, errs
 
 
+def _bytes_only(dtype, B, M, N, K, elems):
+    return 1e-9 * elems + 1e-12 * B * M * N * K
+
+
+@pytest.mark.parametrize("rec", [r for r in TREES if r["name"] in TVALS and len(r["inputs"]) >= 5][::3],
+                         ids=lambda r: r["name"])
+def test_forced_stem_fusion_on_golden_trees(rec):
+    """Stem fusion forced on small golden trees (hyper indices, sliced outputs, preprocessing, lattices):
+    the re-associated plan through the real kernels against the reference's values."""
+    spec = _spec(rec)
+    arrays = make_arrays(spec.shapes(), rec["dtype"], seed=rec["seed"])
+    force = dict(min_big=2, ratio=1.0, min_gain=-1.0, model=_bytes_only)
+    ex = cb.TreeExecutor(spec, dtype=rec["dtype"], fuse=force)
+    got = cb.contract_tree(ex, arrays)
+    assert rel_err(got, TVALS[rec["name"]]) < 1e-10
+    if rec["strip_exponent"]:
+        exs = cb.TreeExecutor(spec, dtype=rec["dtype"], strip_exponent=True, fuse=force)
+        m, e = cb.contract_tree(exs, arrays)
+        assert rel_err(m * 10.0**e, TVALS[rec["name"]]) < 1e-10
+
+
 # ------------------------------------------------------------------ dot-stream 4x4 (peeled stem tail)
 @pytest.mark.parametrize("dtype", ["complex128", "complex64", "float64", "float32"])
 @pytest.mark.parametrize("mn", [(4, 4), (4, 2), (2, 1), (3, 4), (1, 4)])
