@@ -268,6 +268,12 @@ gett_kernel(const int64_t* __restrict__ D, const T* __restrict__ A, const T* __r
     if constexpr (P::CONSUMER_REGS > 0) reg_dealloc<P::PRODUCER_REGS>();
     unsigned ktab_base = 0;
     unsigned g = 0;  // global stage counter
+    // The small operand's tile of a ring slot never changes when there is no n / batch grid and the
+    // k-steps of a work item map onto the slots the same way every time (steps_k divides STAGES):
+    // it is fetched once per slot and stays -- for a K = 16, N = 128 node that is 32 of the 48 KB the
+    // producers would move per tile, all of it the same 32 KB.
+    const bool b_resident = splitk == 1 && n_gn == 0 && n_gb == 0 && steps_k <= (unsigned)STAGES &&
+                            ((unsigned)STAGES % steps_k) == 0;
     for (unsigned j = 0; j < nw; ++j) {
       unsigned k0, k1;
       work_krange(j, k0, k1);
@@ -374,7 +380,9 @@ gett_kernel(const int64_t* __restrict__ D, const T* __restrict__ A, const T* __r
             }
           }
         }
-        if (exactB) {
+        if (b_resident && g >= (unsigned)STAGES) {
+          // (this slot already holds the tile)
+        } else if (exactB) {
 #pragma unroll
           for (int i = 0; i < NB; ++i) {
             const unsigned meta = metaB[i * NPROD + ptid];

@@ -70,8 +70,8 @@ def node_time(dtype, B, M, N, K, elems):
         return _LAUNCH + nbytes / 2.5e12 + flops / 2e12
     if dtype in ("complex128", "float64") and M <= 32 and N <= 32 and B == 1 and K >= 1 << 14:
         # one 32 x 32 DMMA tile, split-K over two CTAs per SM (measured on M = N = 32, K = 2^25:
-        # 3.4 TB/s, 27 TFLOP/s)
-        return _LAUNCH + max(nbytes / 3.6e12, r["flop"] * 32.0 * 32.0 * K / 28e12)
+        # 4.0 TB/s and 32 TFLOP/s at once)
+        return _LAUNCH + max(nbytes / 4.2e12, r["flop"] * 32.0 * 32.0 * K / 33e12)
     if K >= 1 << 12 and (M < 64 or M * N <= 1 << 14):
         # a small result over a long contracted range and no dot-stream kernel for it: a handful
         # of (mostly empty) tensor tiles with split-K atomics -- far from either roofline
