@@ -327,7 +327,7 @@ int tc05_make_tensor_map(const int64_t* h, const void* A, CUtensorMap* tm) {
     if (box[i].ext > 256 || (i && (box[i].stride & 1))) return 0;
     prod *= box[i].ext;
   }
-  if (prod != 128 * 16) return 0;
+  if (prod != (uint64_t)(h[W_MTA] * h[W_KTA])) return 0;
   // base offsets of the tiles: sums of grid-dim digits times even strides, below 2^32 elements
   uint64_t reach = 0;
   auto grid = [&](int off, int n, int width, int col) -> bool {
@@ -366,10 +366,13 @@ int launch_tc05(const int64_t* h, const int64_t* d, const void* A, const void* B
   DevInfo& di = devinfo();
   if (!di.ok) return fail(CTGB_E_CUDA, "no CUDA device");
   auto exact = [&](int pg, int full, int text) { return h[pg] < 0 || (h[full] % h[text]) == 0; };
-  if (h[W_DTYPE] != CTGB_C64 || h[W_MTA] != 128 || h[W_NTA] != NT || h[W_KTA] != 16 ||
+  // every tile has the same shape: the full 128 x NT x 16, or exact divisors of the index extents
+  // (MTa <= 128 rows, NTa <= NT columns, KTa a multiple of 4 up to 16)
+  if (h[W_DTYPE] != CTGB_C64 || h[W_MTA] < 1 || h[W_MTA] > 128 || h[W_NTA] < 1 || h[W_NTA] > NT || h[W_KTA] < 4 ||
+      h[W_KTA] > 16 || (h[W_KTA] & 3) ||
       !exact(W_PGM, W_MFULL, W_MTEXT) || !exact(W_PGN, W_NFULL, W_NTEXT) || !exact(W_PGK, W_KFULL, W_KTEXT) ||
-      h[W_STEPS_K] > KCHUNK || h[W_LBOPAD] < 0 || h[W_LBOPAD] > 4 ||
-      ((h[W_FLAGS] & 64) && (h[W_RUNA] < 16 || (128 * 16) % h[W_RUNA] != 0)))
+      h[W_STEPS_K] > TC05_KTAB || h[W_LBOPAD] < 0 || h[W_LBOPAD] > 4 ||
+      ((h[W_FLAGS] & 64) && (h[W_RUNA] < 16 || (h[W_MTA] * h[W_KTA]) % h[W_RUNA] != 0)))
     return fail(CTGB_E_VALUE, "descriptor does not fit the tcgen05 kernel");
   const uint64_t work = (uint64_t)h[W_TILES_M] * (uint64_t)h[W_TILES_N] * (uint64_t)h[W_TILES_B] * (uint64_t)h[W_SPLITK];
   if (work == 0) return CTGB_OK;

@@ -36,6 +36,15 @@
 // consecutive elements of A's memory order -- hit 16 different 8-byte bank pairs.
 #pragma once
 
+// k-steps (of 16) accumulated in ONE TMEM accumulation: a contracted range of up to 16 steps (K <= 256,
+// every dense Sycamore node) is a single accumulation.  Longer ranges are folded into C by the epilogue
+// chunk by chunk with round-to-nearest adds; the read-modify-write of a chunk hits the C tile the same
+// CTA wrote a moment ago, i.e. L2.  (4-step chunks were measured too: 42.5 instead of 18.6 ms on the
+// bond-6 PEPS tree for no gain in accuracy -- its error came from the truncating operand split.)
+constexpr int TC05_CHUNK = 16;
+// k-steps whose A base offsets are tabulated (the contracted range of one node: K <= 16384)
+constexpr int TC05_KTAB = 1024;
+
 template <int NT_>
 struct Tc05Cfg {
   static constexpr int MT = 128, NT = NT_, KT = 16;
@@ -45,22 +54,19 @@ struct Tc05Cfg {
   static constexpr int A_TILE = MT * KT;                   // float2 elements of one staged A tile
   static constexpr int LBO_BASE = MT * 16;                 // bytes between k chunks of A' (unpadded)
   static constexpr int OP_BYTES = 8 * (LBO_BASE + 64);     // one A' image with the largest padding
-  static constexpr int TMEM_COLS = 4 * NT;                 // fp32 columns of one accumulator: [A'hi B'hi + A'lo B'hi | A'hi B'lo]
+  static constexpr int TMEM_COLS = 4 * NT;                 // fp32 columns of one accumulator: [A'hi B'hi | A'hi B'lo + A'lo B'hi]
   static constexpr int TI = SA_MAX + 4;                    // tile-info ring (epilogue lags <= 2 tiles)
   static constexpr int NBARS = 2 * SA_MAX + 2 * NB_MAX + 2 + 2 + 4;
   static constexpr int THREADS = 14 * 32;
   static_assert(TMEM_COLS == 64 || TMEM_COLS == 128 || TMEM_COLS == 256,
                 "two accumulators: a power of two >= 32 columns each, <= 512 together");
   static constexpr size_t fixed_bytes() {  // everything but the two rings
-    return 4 * (size_t)OP_BYTES + 8 * (size_t)(MT + NT + KCHUNK + 4 * TI + NBARS) + 128;
+    return 4 * (size_t)OP_BYTES + 8 * (size_t)(MT + NT + TC05_KTAB + 4 * TI + NBARS) + 128;
   }
   static constexpr size_t smem_bytes(int sa, int nb) {
     return fixed_bytes() + (size_t)sa * A_TILE * 8 + (size_t)nb * PAIR_BYTES;
   }
 };
-
-// k-steps (of 16) accumulated in TMEM before the epilogue folds them into C (K <= 256 per chunk)
-constexpr int TC05_CHUNK = 16;
 
 // one lane of a converged warp (the compiler keeps the surrounding code warp-uniform)
 __device__ __forceinline__ bool elect_one() {
@@ -99,7 +105,7 @@ tc05_kernel(const int64_t* __restrict__ D, const float2* __restrict__ A, const f
   long long* offMC = reinterpret_cast<long long*>(sB + (size_t)NB * Cfg::PAIR_BYTES);
   long long* offNC = offMC + MT;
   long long* kbA = offNC + NT;
-  long long* ti_base = kbA + KCHUNK;  // [TI][4]: A base, -, C base, -
+  long long* ti_base = kbA + TC05_KTAB;  // [TI][4]: A base, -, C base, -
   unsigned long long* stg_full = reinterpret_cast<unsigned long long*>(ti_base + 4 * TI);
   unsigned long long* stg_empty = stg_full + Cfg::SA_MAX;
   unsigned long long* b_full = stg_empty + Cfg::SA_MAX;
@@ -122,6 +128,14 @@ tc05_kernel(const int64_t* __restrict__ D, const float2* __restrict__ A, const f
   const bool atomic = splitk > 1;
   const bool g_pow2 = (D[W_FLAGS] & 4) != 0;
   const unsigned run_a = (unsigned)D[W_RUNA];
+  // actual tile extents: full 128 x NT x 16 on power-of-two networks; on others (PEPS bond 6) the
+  // host picks exact divisors of the index extents, so every tile has the SAME smaller shape --
+  // rows >= MTa and columns >= NTa of the operand images are padding that the epilogue ignores
+  // (B' is zero there), k >= KTa costs nothing: the UMMAs of the missing k8 groups are not issued
+  const unsigned MTa = (unsigned)D[W_MTA], NTa = (unsigned)D[W_NTA], KTa = (unsigned)D[W_KTA];
+  const unsigned a_elems = MTa * KTa;       // elements of one staged A tile
+  constexpr unsigned chunk = TC05_CHUNK;
+  const unsigned nq = KTa >> 2;             // UMMA k8 groups per k-step (KTa is a multiple of 4)
   // flags bit6: the A tile is made of contiguous runs of run_a elements (>= 128 B, even offsets)
   const bool bulk_a = (D[W_FLAGS] & 64) != 0 && (reinterpret_cast<unsigned long long>(A) & 15ull) == 0;
   const unsigned lbo_a = (unsigned)Cfg::LBO_BASE + 16u * (unsigned)D[W_LBOPAD];
@@ -195,7 +209,7 @@ tc05_kernel(const int64_t* __restrict__ D, const float2* __restrict__ A, const f
       offNC[c] = o;
     }
   } else if (tid < 384) {
-    // A base offset of every k-step (the host guarantees steps_k <= KCHUNK)
+    // A base offset of every k-step (the host guarantees steps_k <= TC05_KTAB)
     for (unsigned s = tid - 256; s < steps_k; s += GROUP) {
       long long a = 0;
       for (int j = 0; j < n_gk; ++j) {
@@ -246,11 +260,12 @@ tc05_kernel(const int64_t* __restrict__ D, const float2* __restrict__ A, const f
   if (warp >= 8 && warp < 12) {
     // ===================================================== A PRODUCERS
     const int ptid = tid - 256;
-    const unsigned nruns = bulk_a ? (unsigned)A_TILE / run_a : 0u;  // <= 128: run_a >= 16
+    const unsigned nruns = bulk_a ? a_elems / run_a : 0u;  // <= 128: run_a >= 16
     constexpr int NG = A_TILE / GROUP;
     long long goff[NG];  // gather mode: element ptid + i*GROUP; bulk mode: goff[0] = start of run ptid
 #pragma unroll
-    for (int i = 0; i < NG; ++i) goff[i] = bulk_a ? 0ll : a_off((unsigned)(ptid + i * GROUP));
+    for (int i = 0; i < NG; ++i)
+      goff[i] = (bulk_a || (unsigned)(ptid + i * GROUP) >= a_elems) ? 0ll : a_off((unsigned)(ptid + i * GROUP));
     if (bulk_a && (unsigned)ptid < nruns) goff[0] = a_off((unsigned)ptid * run_a);
     RingPos ra;
     for (unsigned j = 0; j < nw; ++j) {
@@ -297,7 +312,7 @@ tc05_kernel(const int64_t* __restrict__ D, const float2* __restrict__ A, const f
           // ONE tensor-map TMA copy per k-step (cp.async.bulk.tensor, SASS UTMALDG): the tile is a
           // box of up to four coalesced dims of A in memory order, its position the coordinate of a
           // fifth "offset" dim of stride 16 bytes (tc05_make_tensor_map)
-          const unsigned bytes = ptid == 0 ? (unsigned)A_TILE * 8u : 0u;
+          const unsigned bytes = ptid == 0 ? a_elems * 8u : 0u;
           asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.expect_tx.shared::cta.b64 st, [%0], %1;\n\t}\n" ::"r"(bar),
                        "r"(bytes)
                        : "memory");
@@ -329,7 +344,8 @@ tc05_kernel(const int64_t* __restrict__ D, const float2* __restrict__ A, const f
           }
         } else {
 #pragma unroll
-          for (int i = 0; i < NG; ++i) cp_async_zfill<8>(dst + ptid + i * GROUP, src + goff[i], true);
+          for (int i = 0; i < NG; ++i)
+            if ((unsigned)(ptid + i * GROUP) < a_elems) cp_async_zfill<8>(dst + ptid + i * GROUP, src + goff[i], true);
           mbar_arrive_cp_async(&stg_full[sa]);
         }
       }
@@ -367,7 +383,8 @@ tc05_kernel(const int64_t* __restrict__ D, const float2* __restrict__ A, const f
     constexpr int NSCAT = A_TILE / GROUP;
     unsigned upos[NSCAT];
 #pragma unroll
-    for (int i = 0; i < NSCAT; ++i) upos[i] = a_pos((unsigned)(tid + i * GROUP));
+    for (int i = 0; i < NSCAT; ++i)
+      upos[i] = (unsigned)(tid + i * GROUP) < a_elems ? a_pos((unsigned)(tid + i * GROUP)) : 0xFFFFFFFFu;
     unsigned g = 0;
     RingPos ra;
     for (unsigned j = 0; j < nw; ++j) {
@@ -384,11 +401,19 @@ tc05_kernel(const int64_t* __restrict__ D, const float2* __restrict__ A, const f
         // tile and would otherwise serialise LDS -> STS -> LDS ...
         float2 v[NSCAT];
 #pragma unroll
-        for (int i = 0; i < NSCAT; ++i) v[i] = src[tid + i * GROUP];
+        for (int i = 0; i < NSCAT; ++i) v[i] = upos[i] != 0xFFFFFFFFu ? src[tid + i * GROUP] : make_float2(0.f, 0.f);
 #pragma unroll
         for (int i = 0; i < NSCAT; ++i) {
-          hi2[upos[i]] = v[i];  // the tensor core truncates its operands to tf32 itself
-          lo2[upos[i]] = make_float2(v[i].x - trunc_tf32(v[i].x), v[i].y - trunc_tf32(v[i].y));
+          if (upos[i] != 0xFFFFFFFFu) {
+#ifdef CTGB_TC05_TRUNC_SPLIT  // A/B knob: the cheaper truncating split (biased, see tc05_policy.cuh)
+            hi2[upos[i]] = v[i];
+            lo2[upos[i]] = make_float2(v[i].x - trunc_tf32(v[i].x), v[i].y - trunc_tf32(v[i].y));
+#else
+            const float2 h = make_float2(round_tf32(v[i].x), round_tf32(v[i].y));
+            hi2[upos[i]] = h;
+            lo2[upos[i]] = make_float2(half_up_tf32(v[i].x - h.x), half_up_tf32(v[i].y - h.y));
+#endif
+          }
         }
         asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");  // generic-proxy writes -> tensor core
         __syncwarp();
@@ -403,8 +428,10 @@ tc05_kernel(const int64_t* __restrict__ D, const float2* __restrict__ A, const f
     // InstrDescriptor: D=f32 [4,6)=1, A=tf32 [7,10)=2, B=tf32 [10,13)=2, K-major A/B, N>>3 [17,23), M>>4 [24,29)
     // Two instructions per k8 instead of three passes: B'hi and B'lo are stacked along N, so
     //   [P | Q] (4NT columns)  = A'hi x [B'hi ; B'lo]^T      (A'hi is read from shared memory once)
-    //    P      (2NT columns) += A'lo x  B'hi^T
-    // and the epilogue adds the small term Q to P.
+    //        Q  (2NT columns) += A'lo x  B'hi^T
+    // and the epilogue adds the small terms Q to P.  Both corrections go to Q because the tensor
+    // core truncates its accumulator after every instruction: P, the one that carries the magnitude,
+    // then sees ONE truncation per k8 (measured shrink of a K = 36 node: 6.7e-7 with two).
     constexpr unsigned idesc_wide =
         (1u << 4) | (2u << 7) | (2u << 10) | ((unsigned)((4 * NT) >> 3) << 17) | ((unsigned)(MT >> 4) << 24);
     constexpr unsigned idesc_half =
@@ -419,8 +446,8 @@ tc05_kernel(const int64_t* __restrict__ D, const float2* __restrict__ A, const f
       // a contracted range longer than TC05_CHUNK k-steps (K > 256) is accumulated chunk by chunk:
       // every chunk starts a fresh TMEM accumulation, the epilogue folds it into C with
       // round-to-nearest adds (the tensor core's own accumulation truncates)
-      for (unsigned k0 = kb; k0 < ke; k0 += TC05_CHUNK, ++acq) {
-      const unsigned k1 = min(ke, k0 + (unsigned)TC05_CHUNK);
+      for (unsigned k0 = kb; k0 < ke; k0 += chunk, ++acq) {
+      const unsigned k1 = min(ke, k0 + chunk);
       const unsigned buf = acq & 1;
       mbar_wait(&tmem_empty[buf], ((acq >> 1) & 1) ^ 1);  // the epilogue two accumulations back has drained it
       for (unsigned step = k0; step < k1; ++step, ++g, rb.next(NB)) {
@@ -438,6 +465,7 @@ tc05_kernel(const int64_t* __restrict__ D, const float2* __restrict__ A, const f
         if (elect_one()) {
 #pragma unroll
           for (int q = 0; q < 4; ++q) {
+            if ((unsigned)q >= nq) break;  // (uniform) a tile with fewer than 16 k
             // one UMMA eats K = 8 floats = 2 chunks; chunk stride = LBO, 8-row group stride (SBO) = 128 B
             const uint64_t d_hi = umma_desc_kmajor(a_hi + q * 2 * lbo_a, lbo_a, 128);
             const uint64_t d_lo = umma_desc_kmajor(a_lo + q * 2 * lbo_a, lbo_a, 128);
@@ -450,7 +478,7 @@ tc05_kernel(const int64_t* __restrict__ D, const float2* __restrict__ A, const f
                 : "memory");
             asm volatile(
                 "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-                "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(dcol),
+                "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(dcol + 2 * NT),
                 "l"(d_lo), "l"(d_b), "r"(idesc_half), "r"(1u)
                 : "memory");
           }
@@ -478,13 +506,14 @@ tc05_kernel(const int64_t* __restrict__ D, const float2* __restrict__ A, const f
                          (reinterpret_cast<unsigned long long>(C) & 31ull) == 0;
     const int quad = warp & 3;  // TMEM lane quadrant of this warp
     const int r = quad * 32 + lane;
-    const long long row_off = offMC[r];
+    const bool row_ok = (unsigned)r < MTa;  // padding rows hold whatever the A' images held
+    const long long row_off = row_ok ? offMC[r] : 0ll;
     StripCtx sctx = strip_begin(D);  // fused strip_exponent
     unsigned acq = 0;
     for (unsigned j = 0; j < nw; ++j) {
       unsigned kb, ke;
       work_krange(j, kb, ke);
-      for (unsigned k0 = kb; k0 < ke; k0 += TC05_CHUNK, ++acq) {
+      for (unsigned k0 = kb; k0 < ke; k0 += chunk, ++acq) {
       const unsigned buf = acq & 1;
       const bool rmw = k0 != kb;  // a later chunk of the same tile: add to what the first one stored
       mbar_wait(&tmem_full[buf], (acq >> 1) & 1);
@@ -516,7 +545,7 @@ tc05_kernel(const int64_t* __restrict__ D, const float2* __restrict__ A, const f
         asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
 #pragma unroll
         for (int i = 0; i < 32; ++i) v[i] = __float_as_uint(__uint_as_float(v[i]) + __uint_as_float(u[i]));
-        if (sctx.on) {
+        if (sctx.on && row_ok) {
           if (sctx.scale) {
 #pragma unroll
             for (int i = 0; i < 32; i += 2) {
@@ -539,7 +568,8 @@ tc05_kernel(const int64_t* __restrict__ D, const float2* __restrict__ A, const f
         for (int s4 = 0; s4 < 4; ++s4) {  // groups of 4 complex columns
           const int c0 = (col >> 1) + s4 * 4;
           const unsigned* w = v + s4 * 8;
-          if (quad_ok) {
+          if (!row_ok || (unsigned)c0 >= NTa) continue;
+          if (quad_ok && (unsigned)c0 + 3 < NTa) {
             unsigned x[8];
 #pragma unroll
             for (int e = 0; e < 8; ++e) x[e] = w[e];
@@ -562,6 +592,7 @@ tc05_kernel(const int64_t* __restrict__ D, const float2* __restrict__ A, const f
           } else {
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
+              if ((unsigned)(c0 + e) >= NTa) break;
               float2* p = crow + offNC[c0 + e];
               const float2 val = make_float2(__uint_as_float(w[2 * e]), __uint_as_float(w[2 * e + 1]));
               if (atomic) {

@@ -6,8 +6,8 @@
 // (re, im)-interleaved image and B' is the 2x2-block embedding
 //   B'[2n][2k] = Br   B'[2n][2k+1] = -Bi   B'[2n+1][2k] = Bi   B'[2n+1][2k+1] = Br
 // so that C' is C's own interleaved image.  fp32 accuracy comes from the 3xTF32
-// split  D = (A'hi*B'hi + A'lo*B'hi) + A'hi*B'lo  (the tensor core truncates its
-// operands to tf32, so "hi" is the raw fp32 word and lo = x - trunc_tf32(x)):
+// split  D = A'hi*B'hi + (A'lo*B'hi + A'hi*B'lo)  (hi = rn_tf32(x), lo = rn_tf32(x - hi); the tensor
+// core itself would only truncate, which biases a deep tree):
 // 1.3e-6 relative on a K = 64 tile (scripts/ubench/umma_c64.cu).
 //
 // B' (hi and lo, already in shared-memory tile order: UMMA's K-major no-swizzle
@@ -22,7 +22,18 @@ __device__ __forceinline__ uint64_t umma_desc_kmajor(uint32_t saddr, uint32_t lb
   return (uint64_t)((saddr >> 4) & 0x3FFF) | ((uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16) |
          ((uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32) | ((uint64_t)1 << 46);
 }
+// Round to nearest (ties away) onto the tf32 grid with integer ALU ops.  The tensor core only truncates,
+// and a truncating split (hi = trunc(x), lo = x - hi, lo truncated again by the MMA) biases every product
+// towards zero by ~2^-22: over the dependent nodes of a deep tree that bias adds up linearly (1.7e-5
+// instead of 2.3e-5 on the bond-6 PEPS tree, 2.2e-5 instead of 3.8e-5 on one Sycamore m20 slice once
+// rounded).  cvt.rna.tf32.f32 does the same but costs the scatter pass 13 % (63 instead of 72.6 TFLOP/s on
+// the m20 tree); add + mask are full-rate.  (x within 2^-11 of FLT_MAX would round to inf: not handled.)
 __device__ __forceinline__ float trunc_tf32(float x) { return __uint_as_float(__float_as_uint(x) & 0xFFFFE000u); }
+__device__ __forceinline__ float round_tf32(float x) {
+  return __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xFFFFE000u);
+}
+// the low half: the MMA drops the 13 low bits itself, adding half a tf32 ulp first makes that a rounding
+__device__ __forceinline__ float half_up_tf32(float x) { return __uint_as_float(__float_as_uint(x) + 0x1000u); }
 
 // B -> B'hi / B'lo in shared-memory tile order:
 //   Bp[((ib*tiles_n + in)*steps_k + step)][chunk 0..7][row 0..4NT-1: hi rows, then lo rows][4 floats]
@@ -74,7 +85,13 @@ __global__ void __launch_bounds__(256) bprime_kernel(const int64_t* __restrict__
     // stacked along N: chunk c holds 4NT rows -- rows [0, 2NT) are B'hi, rows [2NT, 4NT) are B'lo --
     // so that one UMMA of N = 4NT multiplies A'hi with both and one of N = 2NT takes B'hi alone
     const unsigned long long base = (idx / TILE) * (2ull * TILE) + ((unsigned long long)chunk * (4 * NT)) * 4 + j;
-    Bp[base + row * 4] = v;                                 // hi: raw fp32 (the tensor core truncates)
-    Bp[base + (row + 2 * NT) * 4] = v - trunc_tf32(v);      // lo
+#ifdef CTGB_TC05_TRUNC_SPLIT  // A/B knob: the truncating split
+    Bp[base + row * 4] = v;
+    Bp[base + (row + 2 * NT) * 4] = v - trunc_tf32(v);
+#else
+    const float vh = round_tf32(v);
+    Bp[base + row * 4] = vh;                                // hi
+    Bp[base + (row + 2 * NT) * 4] = half_up_tf32(v - vh);   // lo (v - vh is exact)
+#endif
   }
 }

@@ -63,7 +63,7 @@ VAR_DMMA3M_128x32, VAR_DMMA3M_256x16, VAR_DMMASTREAM, VAR_DOTSTREAM, VAR_DOTSTRE
 VAR_DMMA_32x32, VAR_ROWSTREAM_K = 18, 19
 DMMASTREAM_MAX_N = 16  # the kernel takes N <= 32, but at N = 32 the staged 256x32 policy is faster (31.8 vs 26 TFLOP/s)
 TC05_VARIANTS = (VAR_TC05_128x64, VAR_TC05_128x32, VAR_TC05_128x16)
-TC05_MAX_K = 2048        # 128 k-steps (the kernel's k table); beyond 256 in chunks of 256
+TC05_MAX_K = 16384       # 1024 k-steps (the kernel's k table); beyond 256 in chunks of 256
 TC05_CHUNK_STEPS = 16    # k-steps (of 16) accumulated in TMEM before a round-to-nearest fold
 # (MT, NT, KT) of every kernel variant -- must match ctg_b200.cu's dispatch
 VARIANT_TILES = {
@@ -259,7 +259,14 @@ def _min_stride(d, cols):
     return min(vals) if vals else 0
 
 
-def split_tile(dims, cols, limit, order_col):
+def _largest_divisor(n, cap):
+    for t in range(min(n, cap), 1, -1):
+        if n % t == 0:
+            return t
+    return 1
+
+
+def split_tile(dims, cols, limit, order_col, exact=False):
     """Pick the tile dims of one class.
 
     Greedy by smallest stride in any operand carrying the dim (those are the
@@ -269,6 +276,9 @@ def split_tile(dims, cols, limit, order_col):
       tile : [[text, *strides]]           local order, partial dim last
       grid : [[count, *strides_per_step]] remaining loops (block dim included)
       partial : (grid_index, full_ext, text, weight) or None
+
+    ``exact``: the blocked dim is cut into equal blocks (the largest divisor of its extent
+    that fits), so that every tile has the same shape -- for kernels without ragged tiles.
     """
     cand = sorted(range(len(dims)), key=lambda i: (_min_stride(dims[i], cols), i))
     tile, used, prod, partial_src = [], set(), 1, None
@@ -282,6 +292,8 @@ def split_tile(dims, cols, limit, order_col):
             prod *= e
         else:
             t = limit // prod
+            if exact:
+                t = _largest_divisor(e, t)
             if t >= 2:
                 rec = list(dims[i])
                 rec[0] = t
@@ -361,14 +373,16 @@ def choose_variant(dtype, B, M, N, K, allow_dmma=True, allow_stream=True, allow_
     # (K > 256 runs in chunks of 256 inside the kernel: every chunk accumulates in TMEM from zero
     # and the epilogue folds it into C with round-to-nearest adds -- the tensor core's own
     # accumulation truncates, which is why a single TMEM accumulation stops at K = 256)
-    if (allow_dmma and allow_tc05 and dtype == "complex64" and M % 128 == 0 and K % 16 == 0
+    if (allow_dmma and allow_tc05 and dtype == "complex64" and M >= 128 and K >= 4 and N >= 12
             and K <= TC05_MAX_K and M * N * K >= 1 << 20):
-        if N % 64 == 0:
+        # (extents need not be powers of two: build_pair_desc cuts every class into EQUAL tiles by
+        # divisors -- 108 x 54 x 12 for the bond-6 PEPS GEMMs -- and falls back to the mma.sync
+        # policy when that leaves the tensor-core tile too empty)
+        if N >= 48:
             return VAR_TC05_128x64
-        if N % 32 == 0:
+        if N >= 24:
             return VAR_TC05_128x32
-        if N % 16 == 0:
-            return VAR_TC05_128x16
+        return VAR_TC05_128x16
     # tensor-core tiles: fp64 DMMA for float64/complex128, 3xTF32 for float32/complex64
     if allow_dmma and M * N * K >= 1 << 15 and M * N >= 1024:
         if dtype == "complex128" and allow_3m and N >= 64 and K >= 64:
@@ -426,12 +440,13 @@ def build_pair_desc(dims: PairDims, dtype, accumulate=False, sm_count=148,
         # tcgen05: every thread of the epilogue owns a whole row, so the rows of a tile need
         # not be neighbours in C -- pick them for the longest contiguous runs of A instead
         # (and B is re-packed by bprime_kernel anyway: only A's strides matter for k too)
-        tm, gm, pm = split_tile(m, (1,), MT, order_col=1)
-        tk, gk, pk = split_tile(k, (1,), KT, order_col=1)
+        tm, gm, pm = split_tile(m, (1,), MT, order_col=1, exact=True)
+        tk, gk, pk = split_tile(k, (1,), KT, order_col=1, exact=True)
+        tn, gn, pn = split_tile(n, (1, 2), NT, order_col=2, exact=True)
     else:
         tm, gm, pm = split_tile(m, (1, 2), MT, order_col=2)
         tk, gk, pk = split_tile(k, (1, 2), KT, order_col=1)
-    tn, gn, pn = split_tile(n, (1, 2), NT, order_col=2)
+        tn, gn, pn = split_tile(n, (1, 2), NT, order_col=2)
     gm, pm = _order_grid(gm, pm, 1)
     gn, pn = _order_grid(gn, pn, 1)
     gk, pk = _order_grid(gk, pk, 1)
@@ -517,9 +532,14 @@ def build_pair_desc(dims: PairDims, dtype, accumulate=False, sm_count=148,
     grid_pow2 = all(is_p2(g[0]) for g in gm + gn + gb)
     m_pow2 = all(is_p2(d[0]) for d in tm) and all(is_p2(g[0]) for g in gm)
     if variant in TC05_VARIANTS:
-        # the tcgen05 kernel only takes exact tiles of its native shape
-        exact = (MTa, NTa, KTa) == (MT, NT, KT) and dtype == "complex64" and all(
-            p is None or p[1] % p[2] == 0 for p in (pm, pn, pk))
+        # the tcgen05 kernel takes tiles of ONE shape: its native 128 x NT x 16, or smaller with
+        # the rest of the tensor-core tile as padding (KTa in steps of 4: whole UMMA k8 groups);
+        # below 40 % occupancy the mma.sync policy is the better choice
+        # (k padding is free -- the UMMAs of missing k8 groups are not issued -- so only rows and columns count)
+        occupancy = (MTa * NTa) / float(MT * NT)
+        exact = (MTa <= MT and NTa <= NT and KTa <= KT and KTa % 4 == 0 and dtype == "complex64"
+                 and occupancy >= 0.4 and steps_k <= 1024
+                 and all(p is None or p[1] % p[2] == 0 for p in (pm, pn, pk)))
         if not exact:
             fb = choose_variant(dtype, B, M, N, K, allow_dmma, allow_tc05=False)
             return build_pair_desc(dims, dtype, accumulate=accumulate, sm_count=sm_count, variant=fb,

@@ -280,6 +280,35 @@ def test_single_operand_long_reductions(eq, shape):
     assert rel_err(got, want) < 1e-10
 
 
+@pytest.mark.parametrize("case", ["peps_top", "matrix_6s", "k_pad", "n_pad_odd"])
+def test_tc05_non_power_of_two_tiles(case):
+    """complex64 on tcgen05 with extents that are not powers of two (PEPS bond 6): every index class
+    is cut into EQUAL tiles by divisors (108 x 54 x 12 for 6^k extents), the rest of the 128 x NT x 16
+    tensor-core tile is padding the epilogue ignores; UMMAs of missing k8 groups are not issued."""
+    rng = np.random.default_rng(11)
+
+    def mk(shape):
+        return (rng.uniform(-1, 1, shape) + 1j * rng.uniform(-1, 1, shape)).astype(np.complex64)
+
+    if case == "peps_top":     # the index pattern of the 46656 x 1296 x 1296 node, two m dims shortened
+        eq, sa, sb = "abcdefgh,bdfgxy->acehxy", (6, 6, 6, 6, 6, 6, 6, 36), (6, 6, 6, 6, 6, 216)
+    elif case == "matrix_6s":
+        eq, sa, sb = "mk,kn->mn", (7776, 216), (216, 216)
+    elif case == "k_pad":      # K = 20 per tile -> KTa = 4 or 20 % ... (divisor tiling of 20 under 16: 10 -> falls back or 4)
+        eq, sa, sb = "mk,kn->mn", (2560, 40), (40, 96)
+    else:                      # N = 54: odd multiple of columns, quads straddle the tile edge
+        eq, sa, sb = "mk,kn->mn", (1296, 72), (72, 54)
+    a, b = mk(sa), mk(sb)
+    got = cb.einsum(eq, a, b)
+    want = orc.einsum(eq, a.astype(np.complex128), b.astype(np.complex128))  # (BLAS behind the oracle's lowering)
+    assert rel_err(got, want) < 1e-5
+    if case in ("peps_top", "matrix_6s"):
+        t, o = L.split_equation(eq)
+        plan = L.build_pair_desc(L.classify_pair(t[0], sa, t[1], sb, o), "complex64", c_dense_elems=want.size)
+        assert plan.variant in L.TC05_VARIANTS
+        assert int(plan.words[L.W_MTA]) == 108 and int(plan.words[L.W_KTA]) == 12
+
+
 # ------------------------------------------------------------------ check_zero
 @pytest.mark.parametrize("name,which", [("lattice6x6_d3_sliced", 0), ("rand_r3_o0_hi0_ho1_root_s666_sliced", 1),
                                         ("lattice4x4_sliced", 1)])
