@@ -381,7 +381,9 @@ int launch_tc05(const int64_t* h, const int64_t* d, const void* A, const void* B
   int dev;
   cudaGetDevice(&dev);
   if (attr_dev != dev) {
-    CUDA_TRY(cudaFuncSetAttribute(tc05_kernel<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    CUDA_TRY(cudaFuncSetAttribute(tc05_kernel<NT, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  (int)di.smem_optin - 1024));
+    CUDA_TRY(cudaFuncSetAttribute(tc05_kernel<NT, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   (int)di.smem_optin - 1024));
     attr_dev = dev;
   }
@@ -431,8 +433,15 @@ int launch_tc05(const int64_t* h, const int64_t* d, const void* A, const void* B
   static const bool tm_off = getenv("CTGB_NO_TENSOR_MAP") != nullptr;
   const int tm_rank = tm_off ? 0 : tc05_make_tensor_map(h, A, &tm);
   if (tm_rank) g_tmap_launches.fetch_add(1, std::memory_order_relaxed);
-  tc05_kernel<NT><<<(unsigned)grid, Cfg::THREADS, smem, st>>>(d, (const float2*)A, Bp, (float2*)C, (unsigned)sa,
-                                                               (unsigned)nb, b_stat, tm, tm_rank);
+  // the lean epilogue: 32-byte quads of a dense, aligned C, no accumulation (see tc05_kernel.cuh)
+  const bool lean = (h[W_FLAGS] & 16) && !(h[W_FLAGS] & 1) && h[W_SPLITK] == 1 &&
+                    (reinterpret_cast<unsigned long long>(C) & 31ull) == 0;
+  if (lean)
+    tc05_kernel<NT, 0><<<(unsigned)grid, Cfg::THREADS, smem, st>>>(d, (const float2*)A, Bp, (float2*)C, (unsigned)sa,
+                                                                    (unsigned)nb, b_stat, tm, tm_rank);
+  else
+    tc05_kernel<NT, 1><<<(unsigned)grid, Cfg::THREADS, smem, st>>>(d, (const float2*)A, Bp, (float2*)C, (unsigned)sa,
+                                                                    (unsigned)nb, b_stat, tm, tm_rank);
   g_launches.fetch_add(1, std::memory_order_relaxed);
   cudaError_t e = cudaGetLastError();
   cudaFreeAsync(Bp, st);
@@ -777,7 +786,9 @@ int ctgb_plan_create(const ctgb_plan_desc* pd, ctgb_plan** out) {
       // so is a tcgen05 node whose contracted range is folded into C chunk by chunk)
       q.measure_after |= w[W_VARIANT] == VAR_KRED;
       q.measure_after |= (w[W_VARIANT] == VAR_TC05_128x64 || w[W_VARIANT] == VAR_TC05_128x32 ||
-                          w[W_VARIANT] == VAR_TC05_128x16) && w[W_STEPS_K] > TC05_CHUNK;
+                          w[W_VARIANT] == VAR_TC05_128x16) &&
+                         tc05_chunk_steps((unsigned)((w[W_STEPS_K] + w[W_SPLITK] - 1) / w[W_SPLITK]),
+                                          (unsigned)(w[W_KTA] >> 2)) < (unsigned)w[W_STEPS_K];
     }
     if (!n.invariant) per_slice += 1 + q.measure_after + (pd->strip_exponent && n.kind == 0 ? 1 : 0);
   }

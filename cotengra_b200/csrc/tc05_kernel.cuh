@@ -42,6 +42,14 @@
 // CTA wrote a moment ago, i.e. L2.  (4-step chunks were measured too: 42.5 instead of 18.6 ms on the
 // bond-6 PEPS tree for no gain in accuracy -- its error came from the truncating operand split.)
 constexpr int TC05_CHUNK = 16;
+// ... balanced (17 full steps are 9 + 8), and shorter in k8 accumulations for tiles with a shorter k (12 on
+// 6^n extents: 12 steps = 36 accumulations): those trees are deep chains of dependent nodes, and with 54
+// accumulations per chunk the bond-6 PEPS amplitude came out at 1.09e-5 instead of 8.8e-6
+__host__ __device__ inline unsigned tc05_chunk_steps(unsigned steps, unsigned nq) {
+  const unsigned cap = nq >= 4u ? (unsigned)TC05_CHUNK : 36u / (nq ? nq : 1u);
+  const unsigned n = (steps + cap - 1) / cap;
+  return n ? (steps + n - 1) / n : 1u;
+}
 // k-steps whose A base offsets are tabulated (the contracted range of one node: K <= 16384)
 constexpr int TC05_KTAB = 1024;
 
@@ -55,7 +63,11 @@ struct Tc05Cfg {
   static constexpr int LBO_BASE = MT * 16;                 // bytes between k chunks of A' (unpadded)
   static constexpr int OP_BYTES = 8 * (LBO_BASE + 64);     // one A' image with the largest padding
   static constexpr int TMEM_COLS = 4 * NT;                 // fp32 columns of one accumulator: [A'hi B'hi | A'hi B'lo + A'lo B'hi]
-  static constexpr int TI = SA_MAX + 4;                    // tile-info ring (epilogue lags <= 2 tiles)
+  // tile-info ring.  With one k-step per tile the A producer runs ahead of the epilogue by the staging
+  // ring (SA) + the scatter of 2 tiles (operand double buffer) + 2 accumulations in TMEM, and it writes
+  // the NEXT tile's entry before it blocks: SA + 5 entries are live.  (SA + 4 was a race on store-bound
+  // single-step nodes, M = 2^25 x 32 x 16: a tile now and then went to another tile's C address.)
+  static constexpr int TI = SA_MAX + 8;
   static constexpr int NBARS = 2 * SA_MAX + 2 * NB_MAX + 2 + 2 + 4;
   static constexpr int THREADS = 14 * 32;
   static_assert(TMEM_COLS == 64 || TMEM_COLS == 128 || TMEM_COLS == 256,
@@ -89,7 +101,7 @@ struct RingPos {
 // SA: depth of the A staging ring.  NB: slots of the B' ring.  b_stat: the B' tiles of this
 // CTA never change (one batch, grid a multiple of tiles_n, steps_k <= NB): they are
 // loaded once into slot = k-step and stay resident.
-template <int NT>
+template <int NT, int EPI>
 __global__ void __launch_bounds__(448, 1)
 tc05_kernel(const int64_t* __restrict__ D, const float2* __restrict__ A, const float* __restrict__ Bp,
             float2* __restrict__ C, const unsigned SA, const unsigned NB, const int b_stat,
@@ -134,7 +146,6 @@ tc05_kernel(const int64_t* __restrict__ D, const float2* __restrict__ A, const f
   // (B' is zero there), k >= KTa costs nothing: the UMMAs of the missing k8 groups are not issued
   const unsigned MTa = (unsigned)D[W_MTA], NTa = (unsigned)D[W_NTA], KTa = (unsigned)D[W_KTA];
   const unsigned a_elems = MTa * KTa;       // elements of one staged A tile
-  constexpr unsigned chunk = TC05_CHUNK;
   const unsigned nq = KTa >> 2;             // UMMA k8 groups per k-step (KTa is a multiple of 4)
   // flags bit6: the A tile is made of contiguous runs of run_a elements (>= 128 B, even offsets)
   const bool bulk_a = (D[W_FLAGS] & 64) != 0 && (reinterpret_cast<unsigned long long>(A) & 15ull) == 0;
@@ -234,6 +245,7 @@ tc05_kernel(const int64_t* __restrict__ D, const float2* __restrict__ A, const f
   const unsigned tiles_all = tiles_m * tiles_n * tiles_b;
   const unsigned total_work = tiles_all * splitk;
   const unsigned steps_per_split = (steps_k + splitk - 1) / splitk;
+  const unsigned chunk = tc05_chunk_steps(steps_per_split, nq);
   const unsigned nw = blockIdx.x < total_work ? (total_work - blockIdx.x + gridDim.x - 1) / gridDim.x : 0u;
   auto work_krange = [&](unsigned j, unsigned& k0, unsigned& k1) {
     const unsigned ks = splitk > 1 ? (blockIdx.x + j * gridDim.x) / tiles_all : 0u;
@@ -504,6 +516,9 @@ tc05_kernel(const int64_t* __restrict__ D, const float2* __restrict__ A, const f
     // ===================================================== EPILOGUE GROUP (warps 4-7)
     const bool quad_ok = (D[W_FLAGS] & 16) != 0 && !accumulate && !atomic &&
                          (reinterpret_cast<unsigned long long>(C) & 31ull) == 0;
+    // (an even but not fourfold tile width, 54 columns on 6^n extents: 16-byte pairs)
+    const bool pair_ok = (D[W_FLAGS] & 32) != 0 && !accumulate && !atomic &&
+                         (reinterpret_cast<unsigned long long>(C) & 15ull) == 0;
     const int quad = warp & 3;  // TMEM lane quadrant of this warp
     const int r = quad * 32 + lane;
     const bool row_ok = (unsigned)r < MTa;  // padding rows hold whatever the A' images held
@@ -515,92 +530,221 @@ tc05_kernel(const int64_t* __restrict__ D, const float2* __restrict__ A, const f
       work_krange(j, kb, ke);
       for (unsigned k0 = kb; k0 < ke; k0 += chunk, ++acq) {
       const unsigned buf = acq & 1;
-      const bool rmw = k0 != kb;  // a later chunk of the same tile: add to what the first one stored
+      // a later chunk of the same tile adds to what the first one stored (accumulating and split-K
+      // launches add every chunk to C anyway)
+      const bool fold = k0 != kb && !accumulate && !atomic;
       mbar_wait(&tmem_full[buf], (acq >> 1) & 1);
       asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
       float2* crow = C + ti_base[(j % TI) * 4 + 2] + row_off;
-      // 32 fp32 columns (16 complex) per tcgen05.ld: one TMEM round trip per 128 bytes of a row
+      // Two epilogues, chosen by the launcher (template parameter EPI): the lean one -- 32-byte quads of a
+      // dense, aligned, non-accumulating C, every dense Sycamore node -- and the general one (16-byte
+      // pairs or single elements, accumulating / split-K launches, and the folds of long contracted
+      // ranges prefetched per column group).  In ONE kernel the general paths cost the single-step
+      // nodes 14 % (instruction fetch: 99 -> 85 TFLOP/s on M = 2^15, N = 1024, K = 64).
+      if constexpr (EPI == 0) {
+        const bool rmw = fold;
+        // 32 fp32 columns (16 complex) per tcgen05.ld: one TMEM round trip per 128 bytes of a row
 #pragma unroll 1
-      for (int col = 0; col < 2 * NT; col += 32) {
-        unsigned v[32];
-        const unsigned ta = taddr + buf * Cfg::TMEM_COLS + ((unsigned)(quad * 32) << 16) + (unsigned)col;
-        asm volatile(
-            "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,"
-            "%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];\n"
-            : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
-              "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
-              "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
-              "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
-            : "r"(ta));
-        // the small term A'hi B'lo sits 2NT columns further
-        unsigned u[32];
-        asm volatile(
-            "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,"
-            "%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];\n"
-            : "=r"(u[0]), "=r"(u[1]), "=r"(u[2]), "=r"(u[3]), "=r"(u[4]), "=r"(u[5]), "=r"(u[6]), "=r"(u[7]), "=r"(u[8]),
-              "=r"(u[9]), "=r"(u[10]), "=r"(u[11]), "=r"(u[12]), "=r"(u[13]), "=r"(u[14]), "=r"(u[15]), "=r"(u[16]),
-              "=r"(u[17]), "=r"(u[18]), "=r"(u[19]), "=r"(u[20]), "=r"(u[21]), "=r"(u[22]), "=r"(u[23]), "=r"(u[24]),
-              "=r"(u[25]), "=r"(u[26]), "=r"(u[27]), "=r"(u[28]), "=r"(u[29]), "=r"(u[30]), "=r"(u[31])
-            : "r"(ta + 2u * NT));
-        asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
+        for (int col = 0; col < 2 * NT; col += 32) {
+          unsigned v[32];
+          const unsigned ta = taddr + buf * Cfg::TMEM_COLS + ((unsigned)(quad * 32) << 16) + (unsigned)col;
+          asm volatile(
+              "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,"
+              "%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];\n"
+              : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+                "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
+                "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
+                "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+              : "r"(ta));
+          // the small terms A'hi B'lo + A'lo B'hi sit 2NT columns further
+          unsigned u[32];
+          asm volatile(
+              "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,"
+              "%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];\n"
+              : "=r"(u[0]), "=r"(u[1]), "=r"(u[2]), "=r"(u[3]), "=r"(u[4]), "=r"(u[5]), "=r"(u[6]), "=r"(u[7]), "=r"(u[8]),
+                "=r"(u[9]), "=r"(u[10]), "=r"(u[11]), "=r"(u[12]), "=r"(u[13]), "=r"(u[14]), "=r"(u[15]), "=r"(u[16]),
+                "=r"(u[17]), "=r"(u[18]), "=r"(u[19]), "=r"(u[20]), "=r"(u[21]), "=r"(u[22]), "=r"(u[23]), "=r"(u[24]),
+                "=r"(u[25]), "=r"(u[26]), "=r"(u[27]), "=r"(u[28]), "=r"(u[29]), "=r"(u[30]), "=r"(u[31])
+              : "r"(ta + 2u * NT));
+          asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
 #pragma unroll
-        for (int i = 0; i < 32; ++i) v[i] = __float_as_uint(__uint_as_float(v[i]) + __uint_as_float(u[i]));
-        if (sctx.on && row_ok) {
-          if (sctx.scale) {
+          for (int i = 0; i < 32; ++i) v[i] = __float_as_uint(__uint_as_float(v[i]) + __uint_as_float(u[i]));
+          if (sctx.on && row_ok) {
+            if (sctx.scale) {
 #pragma unroll
-            for (int i = 0; i < 32; i += 2) {
-              const float2 z = strip_apply(sctx, make_float2(__uint_as_float(v[i]), __uint_as_float(v[i + 1])));
-              v[i] = __float_as_uint(z.x);
-              v[i + 1] = __float_as_uint(z.y);
+              for (int i = 0; i < 32; i += 2) {
+                const float2 z = strip_apply(sctx, make_float2(__uint_as_float(v[i]), __uint_as_float(v[i + 1])));
+                v[i] = __float_as_uint(z.x);
+                v[i + 1] = __float_as_uint(z.y);
+              }
+            } else {
+              // max|C|: integer scan over the 32 words, then (rarely) the values (see gett_ws.cuh)
+              int hmax = 0;
+#pragma unroll
+              for (int i = 0; i < 32; ++i) hmax = max(hmax, (int)(v[i] & 0x7fffffffu));
+              if (strip_hot<float2>(sctx, hmax)) {
+#pragma unroll
+                for (int i = 0; i < 32; i += 2) strip_track_f(sctx, __uint_as_float(v[i]), __uint_as_float(v[i + 1]));
+              }
             }
-          } else {
-            // max|C|: integer scan over the 32 words, then (rarely) the values (see gett_ws.cuh)
-            int hmax = 0;
+          }
 #pragma unroll
-            for (int i = 0; i < 32; ++i) hmax = max(hmax, (int)(v[i] & 0x7fffffffu));
-            if (strip_hot<float2>(sctx, hmax)) {
+          for (int s4 = 0; s4 < 4; ++s4) {  // groups of 4 complex columns
+            const int c0 = (col >> 1) + s4 * 4;
+            const unsigned* w = v + s4 * 8;
+            if (!row_ok || (unsigned)c0 >= NTa) continue;
+            if (quad_ok && (unsigned)c0 + 3 < NTa) {
+              unsigned x[8];
 #pragma unroll
-              for (int i = 0; i < 32; i += 2) strip_track_f(sctx, __uint_as_float(v[i]), __uint_as_float(v[i + 1]));
+              for (int e = 0; e < 8; ++e) x[e] = w[e];
+              if (rmw) {
+                // same thread, same addresses as the chunk before: program order makes the sum visible
+                unsigned long long p0, p1, p2, p3;
+                asm volatile("ld.global.v4.b64 {%0,%1,%2,%3}, [%4];\n" : "=l"(p0), "=l"(p1), "=l"(p2), "=l"(p3) : "l"(crow + offNC[c0]) : "memory");
+                const unsigned long long pp[4] = {p0, p1, p2, p3};
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                  x[2 * e] = __float_as_uint(__uint_as_float(x[2 * e]) + __uint_as_float((unsigned)pp[e]));
+                  x[2 * e + 1] = __float_as_uint(__uint_as_float(x[2 * e + 1]) + __uint_as_float((unsigned)(pp[e] >> 32)));
+                }
+              }
+              const unsigned long long q0 = ((unsigned long long)x[1] << 32) | x[0], q1 = ((unsigned long long)x[3] << 32) | x[2];
+              const unsigned long long q2 = ((unsigned long long)x[5] << 32) | x[4], q3 = ((unsigned long long)x[7] << 32) | x[6];
+              asm volatile("st.global.v4.b64 [%0], {%1,%2,%3,%4};\n" ::"l"(crow + offNC[c0]), "l"(q0), "l"(q1), "l"(q2),
+                           "l"(q3)
+                           : "memory");
+            } else {
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                if ((unsigned)(c0 + e) >= NTa) break;
+                float2* p = crow + offNC[c0 + e];
+                const float2 val = make_float2(__uint_as_float(w[2 * e]), __uint_as_float(w[2 * e + 1]));
+                if (atomic) {
+                  atomic_add_of(p, val);
+                } else if (accumulate || rmw) {
+                  *p = add_of(*p, val);
+                } else {
+                  *p = val;
+                }
+              }
             }
           }
         }
+      } else {
+        // 32 fp32 columns (16 complex) per tcgen05.ld: one TMEM round trip per 128 bytes of a row
+#pragma unroll 1
+        for (int col = 0; col < 2 * NT; col += 32) {
+          // a later chunk adds to what the previous one stored: fetch those 16 complex values FIRST, so
+          // that their L2 latency overlaps the TMEM loads instead of being paid once per vector
+          // (same thread, same addresses as the chunk before: program order makes its stores visible)
+          unsigned long long old[16];
+          if (fold && row_ok) {
 #pragma unroll
-        for (int s4 = 0; s4 < 4; ++s4) {  // groups of 4 complex columns
-          const int c0 = (col >> 1) + s4 * 4;
-          const unsigned* w = v + s4 * 8;
-          if (!row_ok || (unsigned)c0 >= NTa) continue;
-          if (quad_ok && (unsigned)c0 + 3 < NTa) {
-            unsigned x[8];
+            for (int s4 = 0; s4 < 4; ++s4) {
+              const int c0 = (col >> 1) + s4 * 4;
+              unsigned long long* o = old + s4 * 4;
+              if ((unsigned)c0 >= NTa) continue;
+              if (quad_ok && (unsigned)c0 + 3 < NTa) {
+                asm volatile("ld.global.v4.b64 {%0,%1,%2,%3}, [%4];\n" : "=l"(o[0]), "=l"(o[1]), "=l"(o[2]), "=l"(o[3]) : "l"(crow + offNC[c0]) : "memory");
+              } else if (pair_ok) {
 #pragma unroll
-            for (int e = 0; e < 8; ++e) x[e] = w[e];
-            if (rmw) {
-              // same thread, same addresses as the chunk before: program order makes the sum visible
-              unsigned long long p0, p1, p2, p3;
-              asm volatile("ld.global.v4.b64 {%0,%1,%2,%3}, [%4];\n" : "=l"(p0), "=l"(p1), "=l"(p2), "=l"(p3) : "l"(crow + offNC[c0]) : "memory");
-              const unsigned long long pp[4] = {p0, p1, p2, p3};
+                for (int e = 0; e < 4; e += 2)
+                  if ((unsigned)(c0 + e) < NTa)
+                    asm volatile("ld.global.v2.b64 {%0,%1}, [%2];\n" : "=l"(o[e]), "=l"(o[e + 1]) : "l"(crow + offNC[c0 + e]) : "memory");
+              } else {
 #pragma unroll
-              for (int e = 0; e < 4; ++e) {
-                x[2 * e] = __float_as_uint(__uint_as_float(x[2 * e]) + __uint_as_float((unsigned)pp[e]));
-                x[2 * e + 1] = __float_as_uint(__uint_as_float(x[2 * e + 1]) + __uint_as_float((unsigned)(pp[e] >> 32)));
+                for (int e = 0; e < 4; ++e)
+                  if ((unsigned)(c0 + e) < NTa)
+                    asm volatile("ld.global.b64 %0, [%1];\n" : "=l"(o[e]) : "l"(crow + offNC[c0 + e]) : "memory");
               }
             }
-            const unsigned long long q0 = ((unsigned long long)x[1] << 32) | x[0], q1 = ((unsigned long long)x[3] << 32) | x[2];
-            const unsigned long long q2 = ((unsigned long long)x[5] << 32) | x[4], q3 = ((unsigned long long)x[7] << 32) | x[6];
-            asm volatile("st.global.v4.b64 [%0], {%1,%2,%3,%4};\n" ::"l"(crow + offNC[c0]), "l"(q0), "l"(q1), "l"(q2),
-                         "l"(q3)
-                         : "memory");
-          } else {
+          }
+          unsigned v[32];
+          const unsigned ta = taddr + buf * Cfg::TMEM_COLS + ((unsigned)(quad * 32) << 16) + (unsigned)col;
+          asm volatile(
+              "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,"
+              "%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];\n"
+              : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+                "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
+                "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
+                "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+              : "r"(ta));
+          // the small terms A'hi B'lo + A'lo B'hi sit 2NT columns further
+          unsigned u[32];
+          asm volatile(
+              "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,"
+              "%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];\n"
+              : "=r"(u[0]), "=r"(u[1]), "=r"(u[2]), "=r"(u[3]), "=r"(u[4]), "=r"(u[5]), "=r"(u[6]), "=r"(u[7]), "=r"(u[8]),
+                "=r"(u[9]), "=r"(u[10]), "=r"(u[11]), "=r"(u[12]), "=r"(u[13]), "=r"(u[14]), "=r"(u[15]), "=r"(u[16]),
+                "=r"(u[17]), "=r"(u[18]), "=r"(u[19]), "=r"(u[20]), "=r"(u[21]), "=r"(u[22]), "=r"(u[23]), "=r"(u[24]),
+                "=r"(u[25]), "=r"(u[26]), "=r"(u[27]), "=r"(u[28]), "=r"(u[29]), "=r"(u[30]), "=r"(u[31])
+              : "r"(ta + 2u * NT));
+          asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
 #pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              if ((unsigned)(c0 + e) >= NTa) break;
-              float2* p = crow + offNC[c0 + e];
-              const float2 val = make_float2(__uint_as_float(w[2 * e]), __uint_as_float(w[2 * e + 1]));
-              if (atomic) {
-                atomic_add_of(p, val);
-              } else if (accumulate || rmw) {
-                *p = add_of(*p, val);
-              } else {
-                *p = val;
+          for (int i = 0; i < 32; ++i) v[i] = __float_as_uint(__uint_as_float(v[i]) + __uint_as_float(u[i]));
+          if (sctx.on && row_ok) {
+            if (sctx.scale) {
+#pragma unroll
+              for (int i = 0; i < 32; i += 2) {
+                const float2 z = strip_apply(sctx, make_float2(__uint_as_float(v[i]), __uint_as_float(v[i + 1])));
+                v[i] = __float_as_uint(z.x);
+                v[i + 1] = __float_as_uint(z.y);
+              }
+            } else {
+              // max|C|: integer scan over the 32 words, then (rarely) the values (see gett_ws.cuh)
+              int hmax = 0;
+#pragma unroll
+              for (int i = 0; i < 32; ++i) hmax = max(hmax, (int)(v[i] & 0x7fffffffu));
+              if (strip_hot<float2>(sctx, hmax)) {
+#pragma unroll
+                for (int i = 0; i < 32; i += 2) strip_track_f(sctx, __uint_as_float(v[i]), __uint_as_float(v[i + 1]));
+              }
+            }
+          }
+          if (fold && row_ok) {  // (after the strip scaling: what was stored is scaled already)
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+              if ((unsigned)((col >> 1) + i) >= NTa) break;
+              v[2 * i] = __float_as_uint(__uint_as_float(v[2 * i]) + __uint_as_float((unsigned)old[i]));
+              v[2 * i + 1] = __float_as_uint(__uint_as_float(v[2 * i + 1]) + __uint_as_float((unsigned)(old[i] >> 32)));
+            }
+          }
+#pragma unroll
+          for (int s4 = 0; s4 < 4; ++s4) {  // groups of 4 complex columns
+            const int c0 = (col >> 1) + s4 * 4;
+            const unsigned* w = v + s4 * 8;
+            if (!row_ok || (unsigned)c0 >= NTa) continue;
+            if (quad_ok && (unsigned)c0 + 3 < NTa) {
+              unsigned x[8];
+#pragma unroll
+              for (int e = 0; e < 8; ++e) x[e] = w[e];
+              const unsigned long long q0 = ((unsigned long long)x[1] << 32) | x[0], q1 = ((unsigned long long)x[3] << 32) | x[2];
+              const unsigned long long q2 = ((unsigned long long)x[5] << 32) | x[4], q3 = ((unsigned long long)x[7] << 32) | x[6];
+              asm volatile("st.global.v4.b64 [%0], {%1,%2,%3,%4};\n" ::"l"(crow + offNC[c0]), "l"(q0), "l"(q1), "l"(q2),
+                           "l"(q3)
+                           : "memory");
+            } else if (pair_ok) {
+#pragma unroll
+              for (int e = 0; e < 4; e += 2) {
+                if ((unsigned)(c0 + e) >= NTa) break;  // NTa is even here
+                float2* p = crow + offNC[c0 + e];
+                unsigned x[4] = {w[2 * e], w[2 * e + 1], w[2 * e + 2], w[2 * e + 3]};
+                const unsigned long long q0 = ((unsigned long long)x[1] << 32) | x[0], q1 = ((unsigned long long)x[3] << 32) | x[2];
+                asm volatile("st.global.v2.b64 [%0], {%1,%2};\n" ::"l"(p), "l"(q0), "l"(q1) : "memory");
+              }
+            } else {
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                if ((unsigned)(c0 + e) >= NTa) break;
+                float2* p = crow + offNC[c0 + e];
+                const float2 val = make_float2(__uint_as_float(w[2 * e]), __uint_as_float(w[2 * e + 1]));
+                if (atomic) {
+                  atomic_add_of(p, val);
+                } else if (accumulate) {
+                  *p = add_of(*p, val);
+                } else {
+                  *p = val;
+                }
               }
             }
           }

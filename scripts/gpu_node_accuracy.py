@@ -14,9 +14,13 @@ from cotengra_b200 import _lib, lowering as L
 
 config = sys.argv[1] if len(sys.argv) > 1 else "peps8x8"
 spec, _arrays, _ = bench.load_workload(config, "complex64")
-ex = cb.TreeExecutor(spec, dtype="complex64")
-plan = ex.plan
+from cotengra_b200.fusion import fuse_stems
+
 sm = _lib.device_info()["sm_count"]
+spec, _info = fuse_stems(spec, "complex64")  # the tree the executor runs by default
+plan = cb.ExecPlan(spec.contractions(), spec.inputs, spec.output, spec.size_dict, spec.sliced, dtype="complex64",
+                   sm_count=sm)
+only_tc05 = "--tc05" in sys.argv
 lib = _lib.load()
 seen = set()
 for nd in plan.nodes:
@@ -27,7 +31,10 @@ for nd in plan.nodes:
         continue
     seen.add(key)
     B, M, N, K = nd["sizes"]
-    if B * M * K > 2**29 or B * M * N > 2**29:
+    big = "--big" in sys.argv
+    if (B * M * K > 2**29 or B * M * N > 2**29) != big or B * M * N > 2**32:
+        continue
+    if only_tc05 and int(nd["plan"].variant) not in L.TC05_VARIANTS:
         continue
     g = torch.Generator(device="cuda").manual_seed(B + M + N + K)
 
@@ -43,14 +50,25 @@ for nd in plan.nodes:
     for dt, tdt in (("complex64", torch.complex64), ("complex128", torch.complex128)):
         pl = L.build_pair_desc(nd["dims"], dt, sm_count=sm, c_dense_elems=n_c)
         c = torch.full((n_c,), float("nan"), dtype=tdt, device="cuda")
-        x, y = a.to(tdt), b.to(tdt)
+        x, y = (a, b) if tdt == torch.complex64 else (a.to(tdt), b.to(tdt))
         pa, pb = (y, x) if pl.swapped != nd["plan"].swapped else (x, y)
         _lib.check(lib.ctgb_contract_pair(pl.words.ctypes.data, pa.data_ptr(), pb.data_ptr(), c.data_ptr(), 0))
         outs.append((c, pl))
+        torch.cuda.synchronize()
+        del x, y, pa, pb
     torch.cuda.synchronize()
-    got, ref = outs[0][0].to(torch.complex128), outs[1][0]
-    err = (torch.linalg.vector_norm(got - ref) / torch.linalg.vector_norm(ref)).item()
-    mx = ((got - ref).abs().max() / ref.abs().max()).item()
+    got, ref = outs[0][0], outs[1][0]
+    del a, b
+    num = den = dmax = rmax = 0.0
+    for o in range(0, n_c, 2**26):  # in pieces: the operands of the big nodes leave no room for a widened copy
+        d = got[o:o + 2**26].to(torch.complex128) - ref[o:o + 2**26]
+        num += torch.linalg.vector_norm(d).item() ** 2
+        den += torch.linalg.vector_norm(ref[o:o + 2**26]).item() ** 2
+        dmax, rmax = max(dmax, d.abs().max().item()), max(rmax, ref[o:o + 2**26].abs().max().item())
+        del d
+    err, mx = (num / den) ** 0.5, dmax / rmax
     W = outs[0][1].words
+    del got, ref, outs, c
+    torch.cuda.empty_cache()
     print(f"B={B} M={M} N={N} K={K} var={int(W[L.W_VARIANT])} tile=({int(W[L.W_MTA])},{int(W[L.W_NTA])},{int(W[L.W_KTA])}) "
           f"steps_k={int(W[L.W_STEPS_K])} splitk={int(W[L.W_SPLITK])} norm_err={err:.2e} max_err={mx:.2e}", flush=True)
