@@ -309,6 +309,40 @@ def test_tc05_non_power_of_two_tiles(case):
         assert int(plan.words[L.W_MTA]) == 108 and int(plan.words[L.W_KTA]) == 12
 
 
+def test_tc05_single_step_tiles_tile_info_ring():
+    """Store-bound tcgen05 nodes with ONE k-step per tile and ~1800 tiles per CTA (M = 2^24, N = 32,
+    K = 16): the A producer runs SA + 5 tiles ahead of the epilogue, a tile-info ring of SA + 4
+    entries let a tile now and then be stored at another tile's C address (round 2: the m12 tree
+    came out wrong by factors, every node on random operands was right 9 times out of 10).
+    Checked against the FMA kernel on the same operands, three launches."""
+    import torch
+
+    from cotengra_b200 import _lib
+
+    sm = _lib.device_info()["sm_count"]
+    m, n, k = 2**24, 32, 16
+    g = torch.Generator(device="cuda").manual_seed(5)
+    a = torch.empty(m * k, dtype=torch.complex64, device="cuda")
+    b = torch.empty(k * n, dtype=torch.complex64, device="cuda")
+    torch.view_as_real(a).uniform_(-1, 1, generator=g)
+    torch.view_as_real(b).uniform_(-1, 1, generator=g)
+    dims = L.classify_pair("km", (k, m), "kn", (k, n), "mn")
+    outs = []
+    for variant in (None, None, None, L.VAR_SIMT_64x64):
+        plan = L.build_pair_desc(dims, "complex64", variant=variant, c_dense_elems=m * n, sm_count=sm)
+        if variant is None:
+            assert plan.variant in L.TC05_VARIANTS and int(plan.words[L.W_STEPS_K]) == 1
+        c = torch.full((m * n,), float("nan"), dtype=torch.complex64, device="cuda")
+        pa, pb = (b, a) if plan.swapped else (a, b)
+        _lib.check(_lib.load().ctgb_contract_pair(plan.words.ctypes.data, pa.data_ptr(), pb.data_ptr(), c.data_ptr(), 0))
+        outs.append(c)
+    torch.cuda.synchronize()
+    ref = outs[-1]
+    scale = ref.abs().max().item()
+    for c in outs[:-1]:
+        assert ((c - ref).abs().max().item()) < 1e-5 * scale
+
+
 # ------------------------------------------------------------------ check_zero
 @pytest.mark.parametrize("name,which", [("lattice6x6_d3_sliced", 0), ("rand_r3_o0_hi0_ho1_root_s666_sliced", 1),
                                         ("lattice4x4_sliced", 1)])
