@@ -1,5 +1,5 @@
 """Time single pairwise contractions given as einsum equations (dev tool).
-usage: gpu_pair_shapes.py [dtype] -- prints variant, tile, ms and TFLOP/s (8 flops per complex MAC) per case."""
+usage: gpu_pair_shapes.py [dtype] [--only=case] -- prints variant, tile, ms and TFLOP/s (8 flops per complex MAC) per case."""
 import os
 import sys
 
@@ -26,7 +26,10 @@ CASES = [
     ("pow2_k64", "km,kn->mn", (64, 32768), (64, 1024)),
     ("pow2_mk_k1024", "mk,kn->mn", (32768, 1024), (1024, 1024)),
 ]
+only = next((a.split("=")[1] for a in sys.argv if a.startswith("--only=")), None)
 for name, eq, sa, sb in CASES:
+    if only and name != only:
+        continue
     t, o = L.split_equation(eq)
     dims = L.classify_pair(t[0], sa, t[1], sb, o)
     n_c = int(np.prod(dims.out_shape))
