@@ -369,6 +369,10 @@ tc05_kernel(const int64_t* __restrict__ D, const float2* __restrict__ A, const f
     if (lane == 0) {
       RingPos rb;
       const unsigned nwb = b_stat ? min(nw, 1u) : nw;  // resident B': loaded with the first work item only
+      // the pair is chunk-major (k'/4 outermost): a tile with fewer than 16 k uses a PREFIX of it, and only
+      // that is fetched (12 k on 6^n extents: 24 of 32 KB -- B' is 3/4 of what the TMA unit moves on the
+      // 46656 x 1296 x 1296 PEPS node, whose 108 k-steps cannot stay resident)
+      const unsigned pair_bytes = 2u * nq * (4u * NT) * 16u;
       for (unsigned j = 0; j < nwb; ++j) {
         unsigned k0, k1, in_, im_, ib_;
         work_krange(j, k0, k1);
@@ -381,11 +385,11 @@ tc05_kernel(const int64_t* __restrict__ D, const float2* __restrict__ A, const f
           const unsigned dst = (unsigned)__cvta_generic_to_shared(sB + (size_t)sb * Cfg::PAIR_BYTES);
           const char* src = reinterpret_cast<const char*>(Bp) + (tile * steps_k + step) * (unsigned long long)Cfg::PAIR_BYTES;
           asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.expect_tx.shared::cta.b64 st, [%0], %1;\n\t}\n" ::"r"(bar),
-                       "r"(Cfg::PAIR_BYTES)
+                       "r"(pair_bytes)
                        : "memory");
           asm volatile(
               "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::"r"(dst),
-              "l"(src), "r"(Cfg::PAIR_BYTES), "r"(bar)
+              "l"(src), "r"(pair_bytes), "r"(bar)
               : "memory");
         }
       }
