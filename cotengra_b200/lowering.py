@@ -259,14 +259,15 @@ def _min_stride(d, cols):
     return min(vals) if vals else 0
 
 
-def _largest_divisor(n, cap):
+def _largest_divisor(n, cap, prod=1, multiple=1):
+    """Largest divisor t of n, 2 <= t <= cap, with prod * t a multiple of ``multiple`` (1 if none)."""
     for t in range(min(n, cap), 1, -1):
-        if n % t == 0:
+        if n % t == 0 and (prod * t) % multiple == 0:
             return t
     return 1
 
 
-def split_tile(dims, cols, limit, order_col, exact=False):
+def split_tile(dims, cols, limit, order_col, exact=False, multiple=1):
     """Pick the tile dims of one class.
 
     Greedy by smallest stride in any operand carrying the dim (those are the
@@ -278,7 +279,9 @@ def split_tile(dims, cols, limit, order_col, exact=False):
       partial : (grid_index, full_ext, text, weight) or None
 
     ``exact``: the blocked dim is cut into equal blocks (the largest divisor of its extent
-    that fits), so that every tile has the same shape -- for kernels without ragged tiles.
+    that fits), so that every tile has the same shape -- for kernels without ragged tiles;
+    ``multiple``: ... among the divisors that make the tile's extent a multiple of this (the k of a
+    tcgen05 tile is whole UMMA k8 groups of complex numbers: 4).
     """
     cand = sorted(range(len(dims)), key=lambda i: (_min_stride(dims[i], cols), i))
     tile, used, prod, partial_src = [], set(), 1, None
@@ -293,7 +296,7 @@ def split_tile(dims, cols, limit, order_col, exact=False):
         else:
             t = limit // prod
             if exact:
-                t = _largest_divisor(e, t)
+                t = _largest_divisor(e, t, prod, multiple)
             if t >= 2:
                 rec = list(dims[i])
                 rec[0] = t
@@ -441,7 +444,7 @@ def build_pair_desc(dims: PairDims, dtype, accumulate=False, sm_count=148,
         # not be neighbours in C -- pick them for the longest contiguous runs of A instead
         # (and B is re-packed by bprime_kernel anyway: only A's strides matter for k too)
         tm, gm, pm = split_tile(m, (1,), MT, order_col=1, exact=True)
-        tk, gk, pk = split_tile(k, (1,), KT, order_col=1, exact=True)
+        tk, gk, pk = split_tile(k, (1,), KT, order_col=1, exact=True, multiple=4)
         tn, gn, pn = split_tile(n, (1, 2), NT, order_col=2, exact=True)
     else:
         tm, gm, pm = split_tile(m, (1, 2), MT, order_col=2)
@@ -539,6 +542,7 @@ def build_pair_desc(dims: PairDims, dtype, accumulate=False, sm_count=148,
         occupancy = (MTa * NTa) / float(MT * NT)
         exact = (MTa <= MT and NTa <= NT and KTa <= KT and KTa % 4 == 0 and dtype == "complex64"
                  and occupancy >= 0.4 and steps_k <= 1024
+                 and (KTa >= 8 or steps_k == 1)  # many 4-wide k-steps: per-step overhead, mma.sync is better
                  and all(p is None or p[1] % p[2] == 0 for p in (pm, pn, pk)))
         if not exact:
             fb = choose_variant(dtype, B, M, N, K, allow_dmma, allow_tc05=False)

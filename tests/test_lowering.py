@@ -255,3 +255,55 @@ def test_small_result_long_k_descriptors(variant, dtype, mn):
     emulate_pair(plan.words, x.reshape(-1), y.reshape(-1), out)
     want = np.einsum("abmcd,dncab->mn", a, b)
     assert rel_err(out.reshape(M, N), want) < (1e-12 if "128" in dtype or dtype == "float64" else 1e-5)
+
+
+@pytest.mark.parametrize("eq,sa,sb", [
+    ("abcdefgh,bdfgxy->acehxy", (6, 6, 6, 6, 6, 6, 6, 36), (6, 6, 6, 6, 6, 36)),   # the PEPS top-node pattern
+    ("mk,kn->mn", (1296, 216), (216, 216)),
+    ("km,kn->mn", (72, 1296), (72, 54)),
+    ("amb,bna->mn", (3, 640, 12), (12, 96, 3)),                                      # mixed 2^a 3^b 5 extents
+    ("mk,kn->mn", (2560, 40), (40, 96)),
+])
+def test_tcgen05_tiles_on_extents_that_are_not_powers_of_two(eq, sa, sb):
+    """complex64 nodes on 6^n-like extents go to the tcgen05 kernel with EQUAL tiles (divisors of the
+    index classes) inside the 128 x NT x 16 tensor-core tile: the tiles cover the node exactly, fill at
+    least 40 % of the tensor-core tile in M x N, k is a multiple of 4 (whole UMMA k8 groups), and the
+    descriptor addresses the right elements (emulator against einsum)."""
+    a, b = make_arrays([sa, sb], "complex128", seed=3)
+    terms, out = L.split_equation(eq)
+    dims = L.classify_pair(terms[0], sa, terms[1], sb, out)
+    n_out = int(np.prod(dims.out_shape))
+    plan = L.build_pair_desc(dims, "complex64", sm_count=148, c_dense_elems=n_out)
+    assert plan.variant in L.TC05_VARIANTS, plan.variant
+    W = plan.words
+    MT, NT, KT = L.VARIANT_TILES[plan.variant]
+    Bn, M, N, K = plan.sizes
+    MTa, NTa, KTa = int(W[L.W_MTA]), int(W[L.W_NTA]), int(W[L.W_KTA])
+    assert MTa <= MT and NTa <= NT and KTa <= KT and KTa % 4 == 0
+    assert MTa * int(W[L.W_TILES_M]) == M and NTa * int(W[L.W_TILES_N]) == N and KTa * int(W[L.W_STEPS_K]) == K
+    assert MTa * NTa >= 0.4 * MT * NT
+    assert int(W[L.W_STEPS_K]) <= 1024
+    got, _ = run_pair(eq, a.astype(np.complex64), b.astype(np.complex64))
+    assert rel_err(got, np.einsum(eq, a, b)) < 1e-5
+
+
+def test_tcgen05_refuses_what_it_cannot_tile():
+    """Extents without a usable divisor (primes), too few rows or columns, or a contracted range beyond
+    the 1024 tabulated k-steps stay on the staged mma.sync / FMA kernels."""
+    for eq, sa, sb in [("mk,kn->mn", (127 * 4, 64), (64, 64)),       # M = 4 * 127: largest divisor <= 128 is 127 -> ragged k? no: 127 rows ok
+                       ("mk,kn->mn", (1024, 64), (64, 7)),            # N = 7 < 12
+                       ("mk,kn->mn", (64, 64), (64, 64)),             # M < 128
+                       ("mk,kn->mn", (1024, 13), (13, 64)),           # K = 13: no multiple of 4 divides it
+                       ("mk,kn->mn", (256, 32768), (32768, 64))]:     # K > 16384
+        terms, out = L.split_equation(eq)
+        dims = L.classify_pair(terms[0], sa, terms[1], sb, out)
+        plan = L.build_pair_desc(dims, "complex64", sm_count=148, c_dense_elems=int(np.prod(dims.out_shape)))
+        if plan.variant in L.TC05_VARIANTS:
+            # whatever it accepted must still be an exact, sufficiently full tiling
+            W = plan.words
+            MT, NT, _KT = L.VARIANT_TILES[plan.variant]
+            Bn, M, N, K = plan.sizes
+            assert int(W[L.W_MTA]) * int(W[L.W_TILES_M]) == M and int(W[L.W_NTA]) * int(W[L.W_TILES_N]) == N
+            assert int(W[L.W_KTA]) * int(W[L.W_STEPS_K]) == K and int(W[L.W_KTA]) % 4 == 0
+            assert int(W[L.W_MTA]) * int(W[L.W_NTA]) >= 0.4 * MT * NT and int(W[L.W_STEPS_K]) <= 1024
+            assert (eq, sa) == ("mk,kn->mn", (127 * 4, 64)), (eq, sa, sb)
