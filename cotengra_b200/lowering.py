@@ -64,7 +64,8 @@ VAR_DMMA_32x32, VAR_ROWSTREAM_K = 18, 19
 DMMASTREAM_MAX_N = 16  # the kernel takes N <= 32, but at N = 32 the staged 256x32 policy is faster (31.8 vs 26 TFLOP/s)
 TC05_VARIANTS = (VAR_TC05_128x64, VAR_TC05_128x32, VAR_TC05_128x16)
 TC05_MAX_K = 16384       # 1024 k-steps (the kernel's k table); beyond 256 in chunks of 256
-TC05_CHUNK_STEPS = 16    # k-steps (of 16) accumulated in TMEM before a round-to-nearest fold
+TC05_CHUNK_STEPS = 16    # full k-steps accumulated in TMEM before a round-to-nearest fold (tc05_chunk_steps in
+                         # csrc/tc05_kernel.cuh balances the chunks and shortens them for tiles with fewer than 16 k)
 # (MT, NT, KT) of every kernel variant -- must match ctg_b200.cu's dispatch
 VARIANT_TILES = {
     VAR_SIMT_64x64: (64, 64, 8),
