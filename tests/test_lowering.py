@@ -307,3 +307,55 @@ def test_tcgen05_refuses_what_it_cannot_tile():
             assert int(W[L.W_KTA]) * int(W[L.W_STEPS_K]) == K and int(W[L.W_KTA]) % 4 == 0
             assert int(W[L.W_MTA]) * int(W[L.W_NTA]) >= 0.4 * MT * NT and int(W[L.W_STEPS_K]) <= 1024
             assert (eq, sa) == ("mk,kn->mn", (127 * 4, 64)), (eq, sa, sb)
+
+
+def test_tcgen05_random_layouts_on_mixed_radix_extents():
+    """Random permuted layouts with extents drawn from {2, 3, 4, 6, 12}: whenever the lowering hands a
+    complex64 node to the tcgen05 kernel the tiles are exact, every (row, k) position of the real tile is
+    hit exactly once by A's load order, and the emulated data path agrees with einsum."""
+    rng = np.random.default_rng(17)
+    taken = checked = 0
+    for trial in range(60):
+        nm, nk, nn = int(rng.integers(3, 6)), int(rng.integers(1, 4)), int(rng.integers(1, 4))
+        m_ix = [chr(ord("a") + i) for i in range(nm)]
+        k_ix = [chr(ord("A") + i) for i in range(nk)]
+        n_ix = [chr(ord("n") + i) for i in range(nn)]
+        sizes = {c: int(rng.choice([2, 3, 4, 6, 12])) for c in m_ix + k_ix + n_ix}
+        M = int(np.prod([sizes[c] for c in m_ix]))
+        if M < 128 or M > 20000:
+            continue
+        ta = list(rng.permutation(m_ix + k_ix))
+        tb = list(rng.permutation(k_ix + n_ix))
+        out = list(rng.permutation(m_ix + n_ix))
+        sa, sb = tuple(sizes[c] for c in ta), tuple(sizes[c] for c in tb)
+        eq = "".join(ta) + "," + "".join(tb) + "->" + "".join(out)
+        dims = L.classify_pair("".join(ta), sa, "".join(tb), sb, "".join(out))
+        n_out = int(np.prod(dims.out_shape))
+        plan = L.build_pair_desc(dims, "complex64", sm_count=148, c_dense_elems=n_out)
+        if plan.variant not in L.TC05_VARIANTS:
+            continue
+        taken += 1
+        W = plan.words
+        MT, NT, KT = L.VARIANT_TILES[plan.variant]
+        Bn, Mp, Np, Kp = plan.sizes
+        MTa, NTa, KTa = int(W[L.W_MTA]), int(W[L.W_NTA]), int(W[L.W_KTA])
+        assert MTa * int(W[L.W_TILES_M]) == Mp and NTa * int(W[L.W_TILES_N]) == Np and KTa * int(W[L.W_STEPS_K]) == Kp
+        assert KTa % 4 == 0 and MTa <= MT and NTa <= NT and KTa <= KT and MTa * NTa >= 0.4 * MT * NT
+        n_lda = int(W[L.W_NLDA])
+        lda = [tuple(int(x) for x in W[L.OFF_LDA + 4 * i:L.OFF_LDA + 4 * i + 4]) for i in range(n_lda)]
+        pos = set()
+        for e in range(MTa * KTa):
+            r = kk = 0
+            x = e
+            for ext, _s, wr, wk in lda:
+                r += (x % ext) * wr
+                kk += (x % ext) * wk
+                x //= ext
+            pos.add((r, kk))
+        assert len(pos) == MTa * KTa and max(p[0] for p in pos) == MTa - 1 and max(p[1] for p in pos) == KTa - 1
+        if checked < 12:
+            checked += 1
+            a, b = make_arrays([sa, sb], "complex128", seed=trial)
+            got, _ = run_pair(eq, a.astype(np.complex64), b.astype(np.complex64))
+            assert rel_err(got, np.einsum(eq, a, b)) < 1e-5, eq
+    assert taken >= 8 and checked >= 8, (taken, checked)
